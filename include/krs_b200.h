@@ -1,0 +1,209 @@
+/*
+ * krs_b200.h — C ABI of libkrs_b200.so (sm_100a).
+ *
+ * This is the drop-in boundary for the keras-rs hot path
+ *   Embedding gather -> FeatureCross | DotInteraction -> Dense stack (+ BruteForceRetrieval top-k)
+ * The reference (keras-team/keras-rs) has no FFI of its own: its boundary is the Keras Layer
+ * protocol and every FLOP is delegated to keras.ops.  Each entry point below
+ * names the reference call site it replaces (file:line under /root/reference).
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes; no torch / C++ types cross the boundary.
+ *  - every pointer is a DEVICE pointer unless the parameter is documented "host".
+ *  - all matrices are dense row-major fp32; `ld*` are leading dimensions in ELEMENTS.
+ *  - the caller owns every buffer (including workspaces); the library never allocates or frees
+ *    device memory on the hot path (krs_ipc_* setup helpers are the only allocators).
+ *  - calls are asynchronous: work is enqueued on `stream` (a cudaStream_t passed as void*).
+ *  - return value: 0 = KRS_OK, negative = error; text via krs_last_error() (thread-local).
+ *  - functions are re-entrant; no global mutable state except the thread-local error string
+ *    and one-time attribute setup (cudaFuncSetAttribute) guarded by std::call_once.
+ */
+#ifndef KRS_B200_H_
+#define KRS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KRS_OK 0
+#define KRS_EINVAL (-1)   /* bad argument (shape / alignment / enum) */
+#define KRS_ECUDA (-2)    /* CUDA runtime error, see krs_last_error() */
+#define KRS_EUNSUPPORTED (-3)
+#define KRS_ENCCL (-4)
+
+/* ------------------------------------------------------------------ misc */
+int krs_version(void);                 /* 10000*major + 100*minor + patch */
+const char* krs_last_error(void);      /* thread-local, never NULL */
+int krs_device_sm_count(void);         /* SMs of the current device (148 on B200) */
+/* Which GEMM engine the dense contractions use: 0 = fp32 FFMA (exact fp32 products),
+ * 1 = tcgen05 3xTF32 split (tensor pipe, fp32-level accuracy).  Process-wide default. */
+int krs_set_gemm_engine(int engine);
+int krs_get_gemm_engine(void);
+
+/* ------------------------------------------------------------------ activations
+ * keras.activations used as FeatureCross.pre_activation / Dense.activation
+ * (feature_cross.py:115, examples/dcn.py:445, examples/ml_perf/model.py:214-266). */
+enum { KRS_ACT_LINEAR = 0, KRS_ACT_RELU = 1, KRS_ACT_SIGMOID = 2, KRS_ACT_TANH = 3, KRS_ACT_SWISH = 4 };
+
+/* ------------------------------------------------------------------ embedding gather
+ * Replaces keras.layers.Embedding.call == ops.take(table, ids, axis=0) at examples/dcn.py:430-435,
+ * EmbedReduce.call (embed_reduce.py:162-274: weights, sum over axis -2, mean/sum/sqrtn divisors),
+ * the per-feature loop of DistributedEmbedding._default_device_call
+ * (base_distributed_embedding.py:910-928) and the following ops.concatenate
+ * (examples/dcn.py:437, examples/ml_perf/model.py:204-207): ONE launch for all features, output
+ * written directly in the concatenated (B, out_ld) layout. */
+enum { KRS_COMBINER_SUM = 0, KRS_COMBINER_MEAN = 1, KRS_COMBINER_SQRTN = 2 };
+
+typedef struct krs_feature {
+  const float* table;     /* (vocab, dim) fp32 row-major; 16-byte aligned when dim % 4 == 0     */
+  const void* ids;        /* int32 or int64 ids; element (b,h) at ids[b*ids_stride + h]          */
+  const float* weights;   /* NULL or per-id weights, same indexing as ids                        */
+  float* grad;            /* bwd only: dense (vocab, dim) gradient arena, accumulated into       */
+  uint32_t* touched;      /* bwd only: NULL or bitmap of ceil(vocab/32) words, bit r set when    */
+                          /*           row r received gradient                                    */
+  int64_t vocab;          /* rows in table (ids are clamped into [0, vocab-1])                   */
+  int64_t ids_stride;     /* elements between consecutive samples                                */
+  int32_t hotness;        /* H: ids per sample (1 for rank-1 ids)                                */
+  int32_t dim;            /* E                                                                   */
+  int32_t out_offset;     /* first output column of this feature                                 */
+  int32_t combiner;       /* KRS_COMBINER_*                                                      */
+  int32_t ids_i64;        /* 1 = int64 ids, 0 = int32                                            */
+  int32_t reduce;         /* 1 = ids were rank 2 (reduce over H, apply divisor);                 */
+                          /* 0 = rank 1: no reduction, weights only honoured for `sum`           */
+                          /*     (embed_reduce.py:224)                                           */
+  /* row-sharded (MOD) tables, config C5 / SURVEY F6: when num_shards > 1, `shard_tables[s]`     */
+  /* (device array of num_shards pointers, possibly peer-mapped) holds rows r with r%S==s at     */
+  /* local row r/S (tensorflow/distributed_embedding.py:316-328).  `table` is ignored.           */
+  const float* const* shard_tables;
+  float* const* shard_grads;
+  int32_t num_shards;
+  int32_t _pad;
+} krs_feature_t;
+
+/* features: HOST array of F descriptors (copied into kernel parameters; F <= 96 per call).
+ * out: (B, out_ld) fp32. */
+int krs_gather_fwd(const krs_feature_t* features, int F, int64_t B, float* out, int64_t out_ld,
+                   int variant, void* stream);
+/* Backward of the above (a10; oracle jax/test_utils.py:395-417 `grad[col] += w * g[row]`):
+ * scatter-add of gout (B, gout_ld) into each feature's dense `grad` arena, duplicate ids inside a
+ * warp combined with shuffles before one vector atomic per row; sets `touched` bits. */
+int krs_gather_bwd(const krs_feature_t* features, int F, int64_t B, const float* gout,
+                   int64_t gout_ld, void* stream);
+
+/* ------------------------------------------------------------------ FeatureCross (DCN-v2)
+ * Replaces FeatureCross.call, feature_cross.py:155-194:
+ *     h = x            (projection_dim None)      | x @ U      (D,P)
+ *     z = h @ V + b ;  a = pre_activation(z) ;  h2 = a + diag_scale * x ;  y = x0 * h2 + x
+ * x0, x, y, h2: (B, D) row-major, ld = D.  U: (D,P) or NULL.  V: (P or D, D).  b: (D) or NULL.
+ * h2_out (nullable) is saved for the backward; hproj (B,P) workspace/saved, required when U given.
+ * z_out (nullable) receives the pre-activation, required for non-linear activations in training. */
+int krs_cross_fwd(const float* x0, const float* x, const float* U, const float* V, const float* b,
+                  float diag_scale, int act, float* y, float* h2_out, float* z_out, float* hproj,
+                  int64_t B, int D, int P, void* stream);
+/* Backward (analytic).  Outputs: dx0, dx (B,D) [dx0 may alias nothing; if same_input
+ * the caller adds them], dU (D,P) nullable, dV, db nullable.  dz (B,D) and dh (B,P) are caller
+ * workspaces.  dV/dU/db are OVERWRITTEN. */
+int krs_cross_bwd(const float* gy, const float* x0, const float* x, const float* U, const float* V,
+                  const float* h2, const float* z, const float* hproj, float diag_scale, int act,
+                  float* dx0, float* dx, float* dU, float* dV, float* db, float* dz, float* dh,
+                  int64_t B, int D, int P, void* stream);
+/* Elementwise tail only (used when pre_activation is a user callable evaluated by the caller):
+ * y = x0 * (a + diag*x) + x ; and its backward. */
+int krs_cross_combine_fwd(const float* x0, const float* x, const float* a, float diag_scale,
+                          float* y, int64_t n, void* stream);
+int krs_cross_combine_bwd(const float* gy, const float* x0, const float* x, const float* a,
+                          float diag_scale, float* dx0, float* dx, float* da, int64_t n,
+                          void* stream);
+
+/* ------------------------------------------------------------------ Dense
+ * Replaces keras.layers.Dense: y = act(x @ W + b), W is (in, out) (examples/dcn.py:444-447,
+ * examples/ml_perf/model.py:214-266). */
+int krs_dense_fwd(const float* x, const float* W, const float* b, int act, float* y, int64_t B,
+                  int K, int N, void* stream);
+/* dz workspace (B,N).  dx nullable (first layer).  dW, db overwritten. */
+int krs_dense_bwd(const float* gy, const float* x, const float* W, const float* y, int act,
+                  float* dx, float* dW, float* db, float* dz, int64_t B, int K, int N,
+                  void* stream);
+
+/* Plain GEMM, exposed for tests:  C(M,N) = op(A) @ op(B) [+ C if accumulate].
+ * transA: A stored (K,M); transB: B stored (N,K). */
+int krs_sgemm(const float* A, const float* Bm, float* C, int64_t M, int64_t N, int64_t K, int transA,
+              int transB, int accumulate, void* stream);
+
+/* ------------------------------------------------------------------ DotInteraction (DLRM)
+ * Replaces DotInteraction.call, dot_interaction.py:134-205 (stack + bmm + tril take / mask).
+ * feats: HOST array of N device pointers, feature i element (b,e) at feats[i][b*strides[i] + e]
+ * (so slices of a concatenated buffer need no stack copy).  out: (B, out_dim) with
+ * out_dim = N(N-1)/2, N(N+1)/2 (self_interaction) or N*N (skip_gather; upper part exact 0). */
+int krs_dot_fwd(const float* const* feats, const int64_t* strides, int N, int E, int64_t B,
+                int self_interaction, int skip_gather, float* out, void* stream);
+/* dfeats: HOST array of N device pointers with dstrides; dF = (G + G^T) F on the selected set. */
+int krs_dot_bwd(const float* const* feats, const int64_t* strides, const float* gout,
+                float* const* dfeats, const int64_t* dstrides, int N, int E, int64_t B,
+                int self_interaction, int skip_gather, void* stream);
+
+/* ------------------------------------------------------------------ BruteForceRetrieval
+ * Replaces Retrieval.compute_score (retrieval.py:101-117) + keras.ops.top_k + ops.take
+ * (brute_force_retrieval.py:139-143): scores = Q @ C^T are streamed tile by tile and never
+ * materialised; exact top-k, sorted descending, ties -> lowest candidate index first.
+ * Q (nq,d), C (nc,d), cand_ids nullable int32 (nc).  top_scores (nq,k) fp32, top_ids (nq,k) int32.
+ * workspace: krs_topk_workspace_bytes(). */
+size_t krs_topk_workspace_bytes(int64_t nq, int64_t nc, int d, int k);
+int krs_topk(const float* Q, const float* C, const int32_t* cand_ids, float* top_scores,
+             int32_t* top_ids, int64_t nq, int64_t nc, int d, int k, void* workspace,
+             size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ losses
+ * keras.losses.MeanSquaredError / BinaryCrossentropy(from_logits=False) on (B,1) predictions
+ * (examples/dcn.py:128, examples/ml_perf/main.py:201-210): loss scalar (mean over B) and
+ * dpred = dloss/dpred.  kind: 0 = MSE, 1 = BCE on probabilities, 2 = BCE with logits. */
+int krs_loss_fwd_bwd(const float* pred, const float* label, float* loss, float* dpred, int64_t B,
+                     int kind, void* stream);
+
+/* ------------------------------------------------------------------ optimizers (Keras 3 formulas)
+ * AdamW (examples/dcn.py:127):   p -= lr*wd*p ; m += (1-b1)(g-m) ; v += (1-b2)(g*g-v) ;
+ *                                p -= lr*sqrt(1-b2^t)/(1-b1^t) * m / (sqrt(v)+eps)
+ * If `touched` is non-NULL, g is a gradient ARENA: rows whose bit is clear are treated as g = 0
+ * without reading them, set rows are read, zeroed and their bit cleared (row_len = floats per row).
+ * If touched is NULL, g is read densely and left untouched. */
+int krs_adamw(float* p, float* m, float* v, float* g, uint32_t* touched, int64_t n, int row_len,
+              float lr, float b1, float b2, float eps, float wd, int64_t step, void* stream);
+/* Adagrad (examples/ml_perf/main.py:203): acc += g*g ; p -= lr * g / sqrt(acc + eps).
+ * SGD: p -= lr * g.  kind: 0 = SGD, 1 = Adagrad.  Same `touched` arena semantics; with an arena only
+ * touched rows are visited (row-sparse update, identical to the dense update for these rules —
+ * the precedent is jax/embedding_lookup.py:174-273, oracle jax/test_utils.py:474-497). */
+int krs_sgd_adagrad(float* p, float* acc, float* g, uint32_t* touched, int64_t n, int row_len,
+                    float lr, float eps, int kind, void* stream);
+
+/* ------------------------------------------------------------------ MOD shard routing (C5)
+ * owner[i] = ids[i] % S, local[i] = ids[i] / S  (jax/embedding_utils.py:187-197 "MOD";
+ * tensorflow/distributed_embedding.py:316-328) and per-owner counts (S ints, pre-zeroed). */
+int krs_mod_route(const void* ids, int ids_i64, int64_t n, int S, int32_t* owner, int64_t* local,
+                  int32_t* counts, void* stream);
+
+/* ------------------------------------------------------------------ peer memory (setup only)
+ * Row-sharded tables live in cudaMalloc'd arenas exported with cudaIpc so that the fused gather
+ * can read (and the backward can atomically add to) peer shards directly over NVLink. */
+int krs_ipc_alloc(void** dptr, size_t bytes, void* handle_out_64B /*host*/);
+int krs_ipc_open(const void* handle_64B /*host*/, void** dptr);
+int krs_ipc_close(void* dptr);
+int krs_ipc_free(void* dptr);
+int krs_enable_peer_access(int peer_device);
+
+/* NCCL all-to-all (baseline exchange for C5; comm created from a 128-byte unique id). */
+int krs_nccl_unique_id(void* id_out_128B /*host*/);
+int krs_nccl_init(void** comm_out, const void* id_128B /*host*/, int nranks, int rank);
+int krs_nccl_destroy(void* comm);
+/* send/recv counts & displacements in BYTES, host arrays of nranks. */
+int krs_nccl_all_to_all_v(void* comm, const void* sendbuf, const int64_t* send_bytes,
+                          const int64_t* send_displs, void* recvbuf, const int64_t* recv_bytes,
+                          const int64_t* recv_displs, int nranks, void* stream);
+int krs_nccl_all_reduce_sum_f32(void* comm, float* buf, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KRS_B200_H_ */
