@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""bench.py — examples/sec of the DCN-v2 Criteo-shape training step (BASELINE.json configs[1], "C2":
+26 categorical features, vocab 1e6 each, embed_dim 32, batch 65536, 3 full-rank cross layers,
+Dense 192-192-1, MSE, AdamW — the examples/dcn.py wiring) on N B200s, plus the fused embedding-gather
+HBM roofline and the CPU baseline.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  torchrun: python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+One step = gather -> 3x FeatureCross -> MLP -> MSE -> full backward -> embedding scatter-add ->
+AdamW on every parameter (the dense-gradient semantics of the reference: every table row is
+visited).  `value` times K steps with the batch already in HBM; `e2e` times the same step driven
+through the public API from PINNED HOST buffers (H2D of ids+labels and a D2H read of the loss inside
+the timed region).  Inputs are far larger than L2 (3.3 GB of tables, random rows), so no flush is
+needed between iterations ("l2": "inputs_larger_than_L2").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--optimizer", default="adamw", choices=["adamw", "adagrad", "sgd"])
+    ap.add_argument("--engine", default="auto", choices=["auto", "ffma", "tcgen05"])
+    ap.add_argument("--batch", type=int, default=65536)
+    ap.add_argument("--features", type=int, default=26)
+    ap.add_argument("--vocab", type=int, default=1_000_000)
+    ap.add_argument("--embed-dim", type=int, default=32)
+    ap.add_argument("--cross-layers", type=int, default=3)
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather-variant", type=int, default=0)
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"DCN-v2 C2: {a.features} categorical features, vocab {a.vocab} each, embed_dim={a.embed_dim}, "
+            f"batch={a.batch}, {a.cross_layers} full-rank cross layers, Dense 192-192-1, MSE, {a.optimizer}")
+
+
+# --------------------------------------------------------------------------------------- reference arm
+def run_reference(a):
+    """The reference's own CPU path for this workload.  keras/jax cannot be installed here,
+    so this times the oracle PORT (oracle/torch_ref.py: the Keras op sequence one-for-one in torch-CPU),
+    all host threads, each step one full batch of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import torch_ref as T
+    cores = os.cpu_count()
+    r = T.time_cpu_baseline(B=a.batch, F=a.features, V=a.vocab, E=a.embed_dim, L=a.cross_layers, steps=a.steps,
+                            warmup=a.warmup, optimizer=a.optimizer, threads=cores)
+    line = {
+        "impl": "reference", "metric": "examples/sec", "value": r["value"], "unit": "examples/s", "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "global_batch": a.batch},
+        "cpu_baseline": {"value": r["value"], "unit": "examples/s", "cores": cores, "kind": "port",
+                         "sample": f"{a.steps} full steps of batch {a.batch} (torch-CPU restatement of the Keras op "
+                                   "sequence; keras/jax not installable)"},
+        "e2e": {"value": r["value"], "unit": "examples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------- clocks sampler
+class Clocks:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------- our arm
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import keras_rs_b200 as K
+    from keras_rs_b200._lib import check, lib, ptr, stream
+    from keras_rs_b200.dcn import DCN
+
+    engine = a.engine
+    if engine == "auto":
+        engine = os.environ.get("KRS_GEMM_ENGINE", "ffma")
+    K.set_gemm_engine(engine)
+
+    B, F, V, E, L = a.batch, a.features, a.vocab, a.embed_dim, a.cross_layers
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+    if world > 1:
+        from keras_rs_b200.sharded import ShardedDCN
+        model = ShardedDCN([V] * F, embedding_dim=E, num_cross_layers=L, dense_units=(192, 192), seed=1234, rank=rank,
+                           world=world)
+    else:
+        model = DCN([V] * F, embedding_dim=E, num_cross_layers=L, dense_units=(192, 192), seed=1234)
+    opt = {"adamw": lambda: K.optimizers.AdamW(0.01), "adagrad": lambda: K.optimizers.Adagrad(0.01),
+           "sgd": lambda: K.optimizers.SGD(0.01)}[a.optimizer]()
+
+    # synthetic Criteo-shaped data: NB distinct batches, pinned on the host and resident on the device
+    NB = 4
+    g = torch.Generator().manual_seed(1234 + rank)
+    host_ids = [torch.randint(0, V, (B, F), generator=g, dtype=torch.int32).pin_memory() for _ in range(NB)]
+    host_y = [torch.rand((B,), generator=g).pin_memory() for _ in range(NB)]
+    dev_ids = [t.cuda() for t in host_ids]
+    dev_y = [t.cuda() for t in host_y]
+    denom = B * world
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    # ---- device-resident steps ("value") --------------------------------------------------
+    def step_dev(i):
+        model.train_on_batch(dev_ids[i % NB], dev_y[i % NB], opt, denom)
+
+    clocks = Clocks(local)
+    if rank == 0:
+        clocks.start()
+    ms_total = timed(step_dev, a.steps, a.warmup)
+    clk = clocks.stop() if rank == 0 else None
+    ms_step = ms_total / a.steps
+    value = B * world / (ms_step * 1e-3)
+
+    # ---- end-to-end through the public API from pinned host buffers ("e2e") ----------------
+    loss_host = torch.zeros((a.steps + a.warmup + 1,), dtype=torch.float32).pin_memory()
+
+    def step_e2e(i):
+        loss = model.train_on_batch(host_ids[i % NB], host_y[i % NB], opt, denom)
+        loss_host[i % loss_host.numel():i % loss_host.numel() + 1].copy_(loss, non_blocking=True)
+
+    ms_e2e = timed(step_e2e, a.steps, 3) / a.steps
+    e2e_value = B * world / (ms_e2e * 1e-3)
+    h2d = host_ids[0].numel() * 4 + host_y[0].numel() * 4
+    final_loss = float(loss_host[(a.steps + 2) % loss_host.numel()])
+
+    # ---- per-kernel measurements (rank 0 GPU, device resident, CUDA events on the launch stream) ----
+    kern = {}
+    base = model.local if hasattr(model, "local") else model
+    if world == 1:
+        bufs = base._buffers(B)
+        plan = bufs["plan"]
+        out = bufs["xs"][0]
+        s = stream()
+        # distinct id batches per launch so rows are re-fetched from HBM
+        plans = []
+        for i in range(NB):
+            p = K.ops.GatherPlan(base._feature_list(dev_ids[i]))
+            plans.append(p)
+
+        def gather_i(i):
+            p = plans[i % NB]
+            check(lib.krs_gather_fwd(p.arr, p.F, B, ptr(out), base.D, a.gather_variant, s))
+
+        reps = 20
+        ms_g = timed(gather_i, reps, 5) / reps
+        gather_bytes = B * F * E * 4 * 2 + B * F * 4          # rows read + out written + int32 ids
+        kern["gather_fwd"] = {"ms": ms_g, "GBps": gather_bytes / ms_g * 1e-6, "bytes": gather_bytes}
+        c0 = base.cross[0]
+        x0, x1, h2 = bufs["xs"][0], bufs["xs"][1], bufs["h2"][0]
+
+        def cross_i(i):
+            check(lib.krs_cross_fwd(ptr(x0), ptr(x0), None, ptr(c0.kernel), ptr(c0.bias), 0.0, 0, ptr(x1), ptr(h2), None,
+                                    None, B, base.D, 0, s))
+
+        ms_c = timed(cross_i, 5, 2) / 5
+        flops = 2.0 * B * base.D * base.D
+        kern["cross_fwd"] = {"ms": ms_c, "TFLOPs": flops / ms_c * 1e-9, "flops": flops, "engine": engine}
+
+        def adamw_i(i):
+            opt._update(base.emb, base.emb_grad, base.emb_touched)
+
+        ms_a = timed(adamw_i, 5, 2) / 5
+        adam_bytes = base.emb.numel() * 4 * 6
+        kern["adamw_tables"] = {"ms": ms_a, "GBps": adam_bytes / ms_a * 1e-6, "bytes": adam_bytes}
+
+        def scatter_i(i):
+            p = plans[i % NB]
+            for f in range(F):
+                p.arr[f].grad = base.emb_grad[base.row_off[f]:].data_ptr()
+                p.arr[f].touched = base.emb_touched[base.row_off[f] // 32:].data_ptr()
+            check(lib.krs_gather_bwd(p.arr, p.F, B, ptr(bufs["ga"]), base.D, s))
+
+        ms_s = timed(scatter_i, 5, 2) / 5
+        kern["gather_bwd"] = {"ms": ms_s, "GBps": (B * F * E * 4 * 3 + B * F * 4) / ms_s * 1e-6}
+        base.emb_grad.zero_(); base.emb_touched.zero_()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- CPU baseline on the host cores (bounded sample; rank 0, N=1 only) --------------------------
+    cpu = None
+    if world == 1 and not a.no_cpu_baseline:
+        del model
+        torch.cuda.empty_cache()
+        from oracle import torch_ref as T
+        r = T.time_cpu_baseline(B=B, F=F, V=V, E=E, L=L, steps=a.cpu_steps, warmup=1, optimizer=a.optimizer)
+        cpu = {"value": r["value"], "unit": "examples/s", "cores": r["cores"], "kind": "port",
+               "sample": f"{a.cpu_steps} full steps of batch {B} after 1 warm-up (torch-CPU restatement of the Keras "
+                         "op sequence; keras/jax not installable here)", "ms_per_step": r["ms_per_step"]}
+
+    launches_per_step = 1 + L + 3 + 1 + 3 * 3 + 3 * L + 1 + 2
+    roof = None
+    if kern:
+        gk = kern["gather_fwd"]
+        roof = {"kernel": "gather_fast_kernel (fused 26-table gather+concat)", "bound": "hbm", "achieved": gk["GBps"],
+                "peak": hbm_peak, "unit": "GB/s", "frac": gk["GBps"] / hbm_peak, "frac_of_8TBps_nominal": gk["GBps"] / 8000.0,
+                "peak_source": peak_src, "traffic": None, "algorithmic_bytes": gk["bytes"], "ms": gk["ms"]}
+    line = {
+        "metric": "examples/sec", "value": value, "unit": "examples/s", "n_gpus": world, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "global_batch": B * world, "parallelism": f"dp{world}" + (
+            "+mod-row-sharded tables over NVLink peer memory" if world > 1 else ""), "gemm_engine": engine,
+            "l2": "inputs_larger_than_L2", "final_loss": final_loss},
+        "clocks": clk,
+        "e2e": {"value": e2e_value, "unit": "examples/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 4},
+        "gpu_launches": launches_per_step * a.steps,
+        "roofline": roof, "kernels": kern, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -106,10 +106,14 @@ int krs_cross_fwd(const float* x0, const float* x, const float* U, const float* 
 /* Backward (analytic).  Outputs: dx0, dx (B,D) [dx0 may alias nothing; if same_input
  * the caller adds them], dU (D,P) nullable, dV, db nullable.  dz (B,D) and dh (B,P) are caller
  * workspaces.  dV/dU/db are OVERWRITTEN. */
+#define KRS_CROSS_ACC_DX0 1     /* dx0 += gy*h2 instead of dx0 = gy*h2 (stacked layers share x0)   */
+#define KRS_CROSS_SAME_INPUT 2  /* x is x0 (call(x0) with x=None): dx receives the TOTAL gradient    */
+                                /* w.r.t. x0 (incl. whatever dx0 already holds when ACC_DX0 is set);  */
+                                /* dx0 is left holding scratch                                        */
 int krs_cross_bwd(const float* gy, const float* x0, const float* x, const float* U, const float* V,
                   const float* h2, const float* z, const float* hproj, float diag_scale, int act,
                   float* dx0, float* dx, float* dU, float* dV, float* db, float* dz, float* dh,
-                  int64_t B, int D, int P, void* stream);
+                  int64_t B, int D, int P, int flags, void* stream);
 /* Elementwise tail only (used when pre_activation is a user callable evaluated by the caller):
  * y = x0 * (a + diag*x) + x ; and its backward. */
 int krs_cross_combine_fwd(const float* x0, const float* x, const float* a, float diag_scale,
@@ -160,8 +164,10 @@ int krs_topk(const float* Q, const float* C, const int32_t* cand_ids, float* top
  * keras.losses.MeanSquaredError / BinaryCrossentropy(from_logits=False) on (B,1) predictions
  * (examples/dcn.py:128, examples/ml_perf/main.py:201-210): loss scalar (mean over B) and
  * dpred = dloss/dpred.  kind: 0 = MSE, 1 = BCE on probabilities, 2 = BCE with logits. */
+/* denom: normalisation count (<= 0 -> B).  Data-parallel ranks pass the GLOBAL batch so that the
+ * all-reduced loss / gradients are the global-batch mean. */
 int krs_loss_fwd_bwd(const float* pred, const float* label, float* loss, float* dpred, int64_t B,
-                     int kind, void* stream);
+                     int kind, int64_t denom, void* stream);
 
 /* ------------------------------------------------------------------ optimizers (Keras 3 formulas)
  * AdamW (examples/dcn.py:127):   p -= lr*wd*p ; m += (1-b1)(g-m) ; v += (1-b2)(g*g-v) ;

@@ -1,0 +1,24 @@
+#!/bin/bash
+# Builds libkrs_b200.so (+ libkrs_b200_nccl.so) for sm_100a, in-tree.
+set -euo pipefail
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+OUT="$HERE/../lib"
+mkdir -p "$OUT" "$HERE/obj"
+NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
+FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall -Xptxas -v --expt-relaxed-constexpr)
+SRCS=(api gemm_ffma gemm_tc cross_dense gather optim dot topk shard)
+pids=()
+for s in "${SRCS[@]}"; do
+  if [ ! -f "$HERE/obj/$s.o" ] || [ "$HERE/$s.cu" -nt "$HERE/obj/$s.o" ] || [ "$HERE/common.cuh" -nt "$HERE/obj/$s.o" ] || [ "$HERE/../../include/krs_b200.h" -nt "$HERE/obj/$s.o" ]; then
+    ( "$NVCC" "${FLAGS[@]}" -c "$HERE/$s.cu" -o "$HERE/obj/$s.o" > "$HERE/obj/$s.log" 2>&1 || { cat "$HERE/obj/$s.log"; exit 1; } ) &
+    pids+=($!)
+  fi
+done
+for p in "${pids[@]:-}"; do [ -n "$p" ] && wait "$p"; done
+OBJS=()
+for s in "${SRCS[@]}"; do OBJS+=("$HERE/obj/$s.o"); done
+"$NVCC" -shared -o "$OUT/libkrs_b200.so" "${OBJS[@]}" -lcudart -lcuda
+if [ ! -f "$OUT/libkrs_b200_nccl.so" ] || [ "$HERE/nccl_a2a.cu" -nt "$OUT/libkrs_b200_nccl.so" ]; then
+  "$NVCC" "${FLAGS[@]}" -shared "$HERE/nccl_a2a.cu" -o "$OUT/libkrs_b200_nccl.so" -lnccl > "$HERE/obj/nccl.log" 2>&1 || { cat "$HERE/obj/nccl.log"; exit 1; }
+fi
+echo "built $OUT/libkrs_b200.so"

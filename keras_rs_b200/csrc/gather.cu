@@ -1,0 +1,471 @@
+// gather.cu — fused multi-table embedding gather (forward) and scatter-add (backward).
+//
+// Replaces, in ONE launch for all features: keras.layers.Embedding.call == ops.take(table, ids, 0)
+// (examples/dcn.py:430-435), EmbedReduce.call's weights/sum/mean/sqrtn (embed_reduce.py:162-274),
+// the per-feature Python loop of DistributedEmbedding._default_device_call
+// (base_distributed_embedding.py:910-928) and the ops.concatenate that follows
+// (examples/dcn.py:437): rows land directly in the concatenated (B, sum E) activation.
+//
+// HBM-bound integer/byte work: no tensor cores.  What matters is bytes in flight per SM and
+// full-sector accesses:
+//   * fast path (1-hot, uniform E, E/4 a power of two): E/4 lanes per row, 16-byte
+//     ld.global.nc.L1::no_allocate loads, UNROLL independent rows per lane group in flight,
+//     streaming (st.global.cs) stores; the output of consecutive (b,f) items is one contiguous
+//     stream, so stores are perfectly coalesced.
+//   * bulk path (variant 2): rows are staged into shared memory with cp.async.bulk (TMA engine,
+//     mbarrier complete_tx) and each tile leaves with ONE bulk smem->global store.
+//   * generic path: any E / hotness / weights / combiner / MOD-sharded tables.
+// Backward: warp handles 32 consecutive samples of one feature; duplicate ids inside the warp are
+// found with __match_any_sync and their gradient rows summed in registers before one atomic per
+// (row, lane) — the scatter-add oracle is jax/test_utils.py:395-417.
+#include "common.cuh"
+
+namespace krs {
+namespace {
+
+constexpr int MAXF = 96;
+
+struct GatherParams {
+  krs_feature_t f[MAXF];
+  int F;
+  int64_t B;
+  float* out;          // fwd: output ; bwd: gout (const in practice)
+  int64_t out_ld;
+};
+
+template <typename IdT>
+__device__ __forceinline__ int64_t load_id(const void* ids, int64_t idx) {
+  return (int64_t)reinterpret_cast<const IdT*>(ids)[idx];
+}
+__device__ __forceinline__ int64_t clamp_id(int64_t id, int64_t vocab) {
+  return id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+}
+__device__ __forceinline__ const float* row_ptr(const krs_feature_t& f, int64_t id) {
+  if (f.num_shards > 1) {
+    const int s = (int)(id % f.num_shards);
+    return f.shard_tables[s] + (id / f.num_shards) * (int64_t)f.dim;
+  }
+  return f.table + id * (int64_t)f.dim;
+}
+
+// ------------------------------------------------------------------ forward, fast path
+// Requirements (checked on the host): every feature 1-hot, no weights, same dim E = 4*LPR,
+// out_offset = f*E, out_ld = F*E, single shard.  Rows are numbered r = b*F + f.
+template <int LPR, int UNROLL, typename IdT>
+__global__ void __launch_bounds__(256) gather_fast_kernel(const __grid_constant__ GatherParams p) {
+  constexpr int RPW = 32 / LPR;              // rows per warp per step
+  constexpr int E = LPR * 4;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % LPR, rsub = lane / LPR;
+  const int64_t R = p.B * p.F;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t F = (uint32_t)p.F;
+  for (int64_t base = wid * (RPW * UNROLL); base < R; base += nwarps * (RPW * UNROLL)) {
+    const float* src[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int64_t r = base + u * RPW + rsub;
+      src[u] = nullptr;
+      if (r < R) {
+        const int64_t b = r / F;
+        const int f = (int)(r - b * F);
+        const krs_feature_t& ft = p.f[f];
+        const int64_t id = clamp_id(load_id<IdT>(ft.ids, b * ft.ids_stride), ft.vocab);
+        src[u] = ft.table + id * E + sub * 4;
+      }
+    }
+    float4 v[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u)
+      if (src[u]) v[u] = ldg_nc_f4(src[u]);
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int64_t r = base + u * RPW + rsub;
+      if (src[u]) stg_cs_f4(p.out + r * E + sub * 4, v[u]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ forward, bulk-copy (TMA engine) path
+// Same requirements as the fast path.  A CTA owns tiles of TILE_ROWS consecutive output rows; every
+// thread issues cp.async.bulk global->shared for its rows (row = E*4 bytes, multiple of 16), all
+// signalling one mbarrier; after the wait one thread issues a single bulk shared->global store of
+// the whole contiguous tile.  Two tiles are in flight (double buffer).
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  const uint32_t addr = smem_u32(bar);
+  while (!ok) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
+               "r"(bytes)
+               : "memory");
+}
+
+template <typename IdT>
+__global__ void __launch_bounds__(256) gather_bulk_kernel(const __grid_constant__ GatherParams p, int E, int tile_rows) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2];
+  float* tile[2] = {reinterpret_cast<float*>(smem_raw), reinterpret_cast<float*>(smem_raw) + (size_t)tile_rows * E};
+  const int64_t R = p.B * p.F;
+  const int64_t ntiles = (R + tile_rows - 1) / tile_rows;
+  const uint32_t F = (uint32_t)p.F;
+  const uint32_t row_bytes = (uint32_t)E * 4u;
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  uint32_t phase[2] = {0, 0};
+  int it = 0;
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+    const int bsel = it & 1;
+    const int64_t r0 = t * tile_rows;
+    const int nrows = (int)krs::imin<int64_t>(tile_rows, R - r0);
+    // the bulk store that last read this buffer (2 tiles ago) must have finished reading smem
+    if (threadIdx.x == 0) {
+      asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      mbar_expect_tx(&bars[bsel], (uint32_t)nrows * row_bytes);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nrows; i += blockDim.x) {
+      const int64_t r = r0 + i;
+      const int64_t b = r / F;
+      const int f = (int)(r - b * F);
+      const krs_feature_t& ft = p.f[f];
+      const int64_t id = clamp_id(load_id<IdT>(ft.ids, b * ft.ids_stride), ft.vocab);
+      bulk_g2s(tile[bsel] + (size_t)i * E, ft.table + id * E, row_bytes, &bars[bsel]);
+    }
+    mbar_wait(&bars[bsel], phase[bsel]);
+    phase[bsel] ^= 1;
+    if (threadIdx.x == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      bulk_s2g(p.out + r0 * E, tile[bsel], (uint32_t)nrows * row_bytes);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+  if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// ------------------------------------------------------------------ forward, generic path
+// One lane group of `lpr` lanes per (b,f) item; element unit = float4 (VEC) or float.
+template <bool VEC>
+__global__ void __launch_bounds__(256) gather_generic_kernel(const __grid_constant__ GatherParams p, int lpr) {
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % lpr, gsub = lane / lpr;
+  const int groups = 32 / lpr;
+  const int64_t items = p.B * p.F;
+  const int64_t ngroups = (((int64_t)gridDim.x * blockDim.x) >> 5) * groups;
+  const int64_t gid = ((((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * groups) + gsub;
+  constexpr int W = VEC ? 4 : 1;
+  for (int64_t it = gid; it < items; it += ngroups) {
+    const int64_t b = it / p.F;
+    const int f = (int)(it - b * p.F);
+    const krs_feature_t& ft = p.f[f];
+    const int H = ft.hotness;
+    const int nchunk = ft.dim / W;
+    const bool use_w = ft.weights != nullptr && (ft.reduce || ft.combiner == KRS_COMBINER_SUM);  // embed_reduce.py:224
+    // divisor (mean: sum w ; sqrtn: sqrt(sum w^2)); every lane of the group computes it redundantly
+    float div = 1.f;
+    if (ft.reduce && ft.combiner != KRS_COMBINER_SUM) {
+      float d = 0.f;
+      for (int h = 0; h < H; ++h) {
+        const float w = use_w ? ft.weights[b * ft.ids_stride + h] : 1.f;
+        d = (ft.combiner == KRS_COMBINER_MEAN) ? __fadd_rn(d, w) : __fadd_rn(d, __fmul_rn(w, w));
+      }
+      div = (ft.combiner == KRS_COMBINER_MEAN) ? d : sqrtf(d);
+    }
+    float* dst = p.out + b * p.out_ld + ft.out_offset;
+    for (int c = sub; c < nchunk; c += lpr) {
+      float acc[W];
+#pragma unroll
+      for (int j = 0; j < W; ++j) acc[j] = 0.f;
+      for (int h = 0; h < H; ++h) {
+        const int64_t idx = b * ft.ids_stride + h;
+        const int64_t id = clamp_id(ft.ids_i64 ? load_id<int64_t>(ft.ids, idx) : load_id<int32_t>(ft.ids, idx), ft.vocab);
+        const float w = use_w ? ft.weights[idx] : 1.f;
+        const float* src = row_ptr(ft, id) + c * W;
+        float v[W];
+        if (VEC) {
+          float4 t = ldg_nc_f4(src);
+          v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+        } else {
+          v[0] = __ldg(src);
+        }
+        // x = x * w ; sum over axis -2 in order h = 0..H-1 (no FMA contraction: embed_reduce.py:253,261)
+#pragma unroll
+        for (int j = 0; j < W; ++j) acc[j] = (H == 1) ? __fmul_rn(v[j], w) : __fadd_rn(acc[j], __fmul_rn(v[j], w));
+      }
+      if (ft.reduce && ft.combiner != KRS_COMBINER_SUM) {
+#pragma unroll
+        for (int j = 0; j < W; ++j) acc[j] = (div != 0.f) ? __fdiv_rn(acc[j], div) : 0.f;   // divide_no_nan
+      }
+      if (VEC) *reinterpret_cast<float4*>(dst + c * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      else dst[c] = acc[0];
+    }
+  }
+}
+
+// ------------------------------------------------------------------ backward
+// Fast path: 1-hot, no weights (weight 1), any E; warp = 32 consecutive samples of one feature.
+template <typename IdT>
+__global__ void __launch_bounds__(256) scatter_fast_kernel(const __grid_constant__ GatherParams p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nblk = (p.B + 31) >> 5;                 // sample blocks
+  const int64_t items = nblk * p.F;                     // item = (sample block, feature), feature fastest
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const float* __restrict__ gout = p.out;
+  for (int64_t it = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; it < items; it += nwarps) {
+    const int64_t blk = it / p.F;
+    const int f = (int)(it - blk * p.F);
+    const krs_feature_t& ft = p.f[f];
+    const int64_t b0 = blk << 5;
+    const int64_t b = b0 + lane;
+    const bool valid = b < p.B;
+    int64_t id = -1 - lane;                              // unique negative sentinel for tail lanes
+    if (valid) id = clamp_id(load_id<IdT>(ft.ids, b * ft.ids_stride), ft.vocab);
+    const unsigned peers = __match_any_sync(0xffffffffu, id);
+    const bool leader = valid && ((__ffs(peers) - 1) == lane);
+    if (leader && ft.touched) atomicOr(ft.touched + (id >> 5), 1u << (id & 31));
+    const unsigned leaders = __ballot_sync(0xffffffffu, leader);
+    const int E = ft.dim;
+    for (unsigned m = leaders; m; m &= m - 1) {
+      const int r = __ffs(m) - 1;
+      const int64_t rid = __shfl_sync(0xffffffffu, id, r);
+      const unsigned rp = __shfl_sync(0xffffffffu, peers, r);
+      float* drow;
+      if (ft.num_shards > 1) drow = ft.shard_grads[(int)(rid % ft.num_shards)] + (rid / ft.num_shards) * (int64_t)E;
+      else drow = ft.grad + rid * (int64_t)E;
+      for (int c = lane; c < E; c += 32) {
+        float acc = 0.f;
+        for (unsigned q = rp; q; q &= q - 1) {
+          const int j = __ffs(q) - 1;
+          acc += gout[(b0 + j) * p.out_ld + ft.out_offset + c];
+        }
+        atomicAdd(drow + c, acc);
+      }
+    }
+  }
+}
+
+// Generic: warp per (b,f) item, loops over hotness; coefficient = w / divisor.
+__global__ void __launch_bounds__(256) scatter_generic_kernel(const __grid_constant__ GatherParams p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t items = p.B * p.F;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const float* __restrict__ gout = p.out;
+  for (int64_t it = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; it < items; it += nwarps) {
+    const int64_t b = it / p.F;
+    const int f = (int)(it - b * p.F);
+    const krs_feature_t& ft = p.f[f];
+    const int H = ft.hotness, E = ft.dim;
+    const bool use_w = ft.weights != nullptr && (ft.reduce || ft.combiner == KRS_COMBINER_SUM);
+    float scale = 1.f;
+    if (ft.reduce && ft.combiner != KRS_COMBINER_SUM) {
+      float d = 0.f;
+      for (int h = 0; h < H; ++h) {
+        const float w = use_w ? ft.weights[b * ft.ids_stride + h] : 1.f;
+        d += (ft.combiner == KRS_COMBINER_MEAN) ? w : w * w;
+      }
+      if (ft.combiner == KRS_COMBINER_SQRTN) d = sqrtf(d);
+      scale = d != 0.f ? 1.f / d : 0.f;
+    }
+    const float* g = gout + b * p.out_ld + ft.out_offset;
+    for (int h = 0; h < H; ++h) {
+      const int64_t idx = b * ft.ids_stride + h;
+      const int64_t id = clamp_id(ft.ids_i64 ? load_id<int64_t>(ft.ids, idx) : load_id<int32_t>(ft.ids, idx), ft.vocab);
+      const float coef = (use_w ? ft.weights[idx] : 1.f) * scale;
+      if (coef == 0.f) continue;
+      float* drow;
+      if (ft.num_shards > 1) drow = ft.shard_grads[(int)(id % ft.num_shards)] + (id / ft.num_shards) * (int64_t)E;
+      else drow = ft.grad + id * (int64_t)E;
+      if (lane == 0 && ft.touched) atomicOr(ft.touched + (id >> 5), 1u << (id & 31));
+      for (int c = lane; c < E; c += 32) atomicAdd(drow + c, coef * g[c]);
+    }
+  }
+}
+
+int fill_params(GatherParams& p, const krs_feature_t* features, int F, int64_t B, float* out, int64_t out_ld) {
+  KRS_REQUIRE(features != nullptr && F > 0 && F <= MAXF, "gather: need 1..%d features per call, got %d", MAXF, F);
+  KRS_REQUIRE(B >= 0, "gather: negative batch");
+  for (int i = 0; i < F; ++i) {
+    const krs_feature_t& f = features[i];
+    KRS_REQUIRE(f.ids != nullptr, "gather: feature %d has null ids", i);
+    KRS_REQUIRE(f.dim > 0 && f.hotness > 0 && f.vocab > 0, "gather: feature %d has bad dim/hotness/vocab", i);
+    KRS_REQUIRE(f.combiner >= 0 && f.combiner <= 2, "gather: feature %d has unknown combiner %d", i, f.combiner);
+    KRS_REQUIRE(f.out_offset >= 0 && f.out_offset + f.dim <= out_ld, "gather: feature %d columns exceed out_ld", i);
+    KRS_REQUIRE(f.num_shards <= 1 || f.shard_tables != nullptr || f.shard_grads != nullptr,
+                "gather: feature %d is sharded but has no shard pointer array", i);
+    p.f[i] = f;
+  }
+  p.F = F;
+  p.B = B;
+  p.out = out;
+  p.out_ld = out_ld;
+  return KRS_OK;
+}
+
+bool uniform_onehot(const GatherParams& p, int* E_out, bool* i64) {
+  const int E = p.f[0].dim;
+  const int is64 = p.f[0].ids_i64;
+  for (int i = 0; i < p.F; ++i) {
+    const krs_feature_t& f = p.f[i];
+    if (f.hotness != 1 || f.dim != E || f.ids_i64 != is64 || f.num_shards > 1) return false;
+    if (f.weights != nullptr && (f.reduce || f.combiner == KRS_COMBINER_SUM)) return false;
+    if (f.out_offset != i * E) return false;
+    if (f.table == nullptr || !aligned16(f.table)) return false;
+  }
+  if (p.out_ld != (int64_t)p.F * E || !aligned16(p.out)) return false;
+  *E_out = E;
+  *i64 = is64 != 0;
+  return true;
+}
+
+template <int LPR, typename IdT>
+int launch_fast(const GatherParams& p, cudaStream_t s) {
+  constexpr int UNROLL = (LPR >= 16) ? 4 : 8;
+  const int64_t R = p.B * p.F;
+  const int64_t rows_per_warp_step = (32 / LPR) * UNROLL;
+  const int64_t warps_needed = ceil_div<int64_t>(R, rows_per_warp_step);
+  const int64_t blocks_needed = ceil_div<int64_t>(warps_needed, 8);
+  const int64_t cap = (int64_t)sm_count() * 8 * 4;        // up to 4 grid-stride trips beyond full residency
+  const unsigned grid = (unsigned)krs::imax<int64_t>(1, min(blocks_needed, cap));
+  gather_fast_kernel<LPR, UNROLL, IdT><<<grid, 256, 0, s>>>(p);
+  KRS_LAUNCH_CHECK();
+  return KRS_OK;
+}
+
+template <typename IdT>
+int launch_bulk(const GatherParams& p, int E, cudaStream_t s) {
+  // two tiles of ~48 KB each
+  int tile_rows = (48 * 1024) / (E * 4);
+  if (tile_rows < 1) return KRS_EUNSUPPORTED;
+  const size_t smem = (size_t)2 * tile_rows * E * 4;
+  static bool attr_done = false;
+  if (!attr_done) {
+    KRS_CUDA(cudaFuncSetAttribute(gather_bulk_kernel<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    KRS_CUDA(cudaFuncSetAttribute(gather_bulk_kernel<int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_done = true;
+  }
+  const int64_t R = p.B * p.F;
+  const int64_t ntiles = ceil_div<int64_t>(R, tile_rows);
+  const unsigned grid = (unsigned)krs::imax<int64_t>(1, krs::imin<int64_t>(ntiles, (int64_t)sm_count() * 2));
+  gather_bulk_kernel<IdT><<<grid, 256, smem, s>>>(p, E, tile_rows);
+  KRS_LAUNCH_CHECK();
+  return KRS_OK;
+}
+
+}  // namespace
+}  // namespace krs
+
+using namespace krs;
+
+extern "C" int krs_gather_fwd(const krs_feature_t* features, int F, int64_t B, float* out, int64_t out_ld, int variant,
+                              void* stream) {
+  GatherParams p;
+  int rc = fill_params(p, features, F, B, out, out_ld);
+  if (rc) return rc;
+  KRS_REQUIRE(out != nullptr, "krs_gather_fwd: null output");
+  for (int i = 0; i < F; ++i)
+    KRS_REQUIRE(p.f[i].num_shards > 1 ? p.f[i].shard_tables != nullptr : p.f[i].table != nullptr,
+                "krs_gather_fwd: feature %d has no table", i);
+  if (B == 0) return KRS_OK;
+  cudaStream_t s = as_stream(stream);
+  int E = 0;
+  bool i64 = false;
+  const bool fast_ok = uniform_onehot(p, &E, &i64) && (E % 4 == 0) && ((E / 4) & (E / 4 - 1)) == 0 && E <= 128;
+  KRS_REQUIRE(variant >= 0 && variant <= 3, "krs_gather_fwd: unknown variant %d", variant);
+  if ((variant == 1 || variant == 2) && !fast_ok) {
+    set_error("krs_gather_fwd: variant %d needs 1-hot features of one dim E in {4,8,16,32,64,128}", variant);
+    return KRS_EUNSUPPORTED;
+  }
+  if (variant == 2) return i64 ? launch_bulk<int64_t>(p, E, s) : launch_bulk<int32_t>(p, E, s);
+  if (fast_ok && variant != 3) {
+#define KRS_FAST(L)                                                              \
+  case L:                                                                        \
+    return i64 ? launch_fast<L, int64_t>(p, s) : launch_fast<L, int32_t>(p, s);
+    switch (E / 4) {
+      KRS_FAST(1)
+      KRS_FAST(2)
+      KRS_FAST(4)
+      KRS_FAST(8)
+      KRS_FAST(16)
+      KRS_FAST(32)
+    }
+#undef KRS_FAST
+  }
+  // generic
+  int maxE = 0;
+  bool vec = aligned16(out) && (out_ld % 4 == 0);
+  for (int i = 0; i < F; ++i) {
+    maxE = max(maxE, p.f[i].dim);
+    if (p.f[i].dim % 4 != 0 || p.f[i].out_offset % 4 != 0) vec = false;
+    if (p.f[i].num_shards <= 1 && !aligned16(p.f[i].table)) vec = false;
+  }
+  const int chunks = vec ? maxE / 4 : maxE;
+  int lpr = 1;
+  while (lpr < chunks && lpr < 32) lpr <<= 1;
+  const int64_t items = B * F;
+  const int64_t warps_needed = ceil_div<int64_t>(items, 32 / lpr);
+  const unsigned grid = (unsigned)krs::imax<int64_t>(1, krs::imin<int64_t>(ceil_div<int64_t>(warps_needed, 8), (int64_t)sm_count() * 32));
+  if (vec) gather_generic_kernel<true><<<grid, 256, 0, s>>>(p, lpr);
+  else gather_generic_kernel<false><<<grid, 256, 0, s>>>(p, lpr);
+  KRS_LAUNCH_CHECK();
+  return KRS_OK;
+}
+
+extern "C" int krs_gather_bwd(const krs_feature_t* features, int F, int64_t B, const float* gout, int64_t gout_ld,
+                              void* stream) {
+  GatherParams p;
+  int rc = fill_params(p, features, F, B, const_cast<float*>(gout), gout_ld);
+  if (rc) return rc;
+  KRS_REQUIRE(gout != nullptr, "krs_gather_bwd: null gradient");
+  bool fast = true;
+  const int is64 = p.f[0].ids_i64;
+  for (int i = 0; i < F; ++i) {
+    const krs_feature_t& f = p.f[i];
+    KRS_REQUIRE(f.num_shards > 1 ? f.shard_grads != nullptr : f.grad != nullptr,
+                "krs_gather_bwd: feature %d has no gradient arena", i);
+    if (f.hotness != 1 || f.ids_i64 != is64) fast = false;
+    if (f.weights != nullptr && (f.reduce || f.combiner == KRS_COMBINER_SUM)) fast = false;
+  }
+  if (B == 0) return KRS_OK;
+  cudaStream_t s = as_stream(stream);
+  if (fast) {
+    const int64_t items = ceil_div<int64_t>(B, 32) * F;
+    const unsigned grid = (unsigned)krs::imax<int64_t>(1, krs::imin<int64_t>(ceil_div<int64_t>(items, 8), (int64_t)sm_count() * 16));
+    if (is64) scatter_fast_kernel<int64_t><<<grid, 256, 0, s>>>(p);
+    else scatter_fast_kernel<int32_t><<<grid, 256, 0, s>>>(p);
+  } else {
+    const int64_t items = B * F;
+    const unsigned grid = (unsigned)krs::imax<int64_t>(1, krs::imin<int64_t>(ceil_div<int64_t>(items, 8), (int64_t)sm_count() * 32));
+    scatter_generic_kernel<<<grid, 256, 0, s>>>(p);
+  }
+  KRS_LAUNCH_CHECK();
+  return KRS_OK;
+}

@@ -1,0 +1,192 @@
+// optim.cu — optimizer sweeps for the hot path's parameters (Keras 3 update rules).
+//
+// AdamW (examples/dcn.py:127) has to visit every row of every table each step (moment decay and
+// decoupled weight decay touch untouched rows too — that is what the reference's dense-gradient
+// path does), so it is a pure HBM streaming kernel: read p,m,v (+g for touched rows), write p,m,v.
+// The gradient "arena" + touched bitmap written by krs_gather_bwd lets the sweep skip reading the
+// (V,E) gradient for rows that received none (g = 0 there), and re-zeroes what it consumed, so no
+// separate 3.3 GB zero-fill or dense-gradient read is ever paid.
+// SGD / Adagrad (examples/ml_perf/main.py:203) have zero update where g = 0, so with an arena they
+// walk only the touched rows — exactly equal to the dense update
+// (precedent: jax/embedding_lookup.py:174-273; oracle jax/test_utils.py:474-497).
+#include <math.h>
+
+#include "common.cuh"
+
+namespace krs {
+namespace {
+
+struct AdamArgs {
+  float lr, b1, b2, eps, wd, alpha;   // alpha = lr * sqrt(1-b2^t)/(1-b1^t)
+};
+
+__device__ __forceinline__ void adamw_one(float& p, float& m, float& v, float g, const AdamArgs& a) {
+  p = p - p * a.wd * a.lr;                 // decoupled decay (Keras: variable -= variable * wd * lr)
+  m = m + (g - m) * (1.f - a.b1);
+  v = v + (g * g - v) * (1.f - a.b2);
+  p = p - (m * a.alpha) / (sqrtf(v) + a.eps);
+}
+
+// One thread per float4.  VEC4 requires n % 4 == 0, row_len % 4 == 0 and 16-byte alignment.
+template <bool ARENA>
+__global__ void __launch_bounds__(256) adamw_vec_kernel(float* __restrict__ p, float* __restrict__ m,
+                                                        float* __restrict__ v, float* __restrict__ g,
+                                                        const uint32_t* __restrict__ touched, int64_t n4, int row_len4,
+                                                        AdamArgs a) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 gp = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ARENA) {
+      const int64_t row = i / row_len4;
+      if ((touched[row >> 5] >> (row & 31)) & 1u) {
+        gp = reinterpret_cast<float4*>(g)[i];
+        reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    } else {
+      gp = reinterpret_cast<const float4*>(g)[i];
+    }
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    adamw_one(pp.x, mm.x, vv.x, gp.x, a);
+    adamw_one(pp.y, mm.y, vv.y, gp.y, a);
+    adamw_one(pp.z, mm.z, vv.z, gp.z, a);
+    adamw_one(pp.w, mm.w, vv.w, gp.w, a);
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+  }
+}
+
+template <bool ARENA>
+__global__ void __launch_bounds__(256) adamw_scalar_kernel(float* __restrict__ p, float* __restrict__ m,
+                                                           float* __restrict__ v, float* __restrict__ g,
+                                                           const uint32_t* __restrict__ touched, int64_t n, int row_len,
+                                                           AdamArgs a) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float gp = 0.f;
+    if (ARENA) {
+      const int64_t row = i / row_len;
+      if ((touched[row >> 5] >> (row & 31)) & 1u) {
+        gp = g[i];
+        g[i] = 0.f;
+      }
+    } else {
+      gp = g[i];
+    }
+    float pp = p[i], mm = m[i], vv = v[i];
+    adamw_one(pp, mm, vv, gp, a);
+    p[i] = pp;
+    m[i] = mm;
+    v[i] = vv;
+  }
+}
+
+// Row-sparse SGD / Adagrad over the touched bitmap.  Each lane fetches one bitmap word (coalesced),
+// then the warp walks the set bits of the 32 words together; a row is updated by the whole warp
+// (lanes stride the row).  The word is cleared afterwards by its owner lane.
+__global__ void __launch_bounds__(256) sparse_rows_kernel(float* __restrict__ p, float* __restrict__ acc,
+                                                          float* __restrict__ g, uint32_t* __restrict__ touched,
+                                                          int64_t nwords, int64_t nrows, int row_len, float lr,
+                                                          float eps, int kind) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t w0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; w0 < nwords; w0 += nwarps * 32) {
+    const int64_t wi = w0 + lane;
+    uint32_t word = wi < nwords ? touched[wi] : 0u;
+    unsigned nz = __ballot_sync(0xffffffffu, word != 0u);
+    while (nz) {
+      const int src = __ffs(nz) - 1;
+      nz &= nz - 1;
+      uint32_t bits = __shfl_sync(0xffffffffu, word, src);
+      while (bits) {
+        const int bit = __ffs(bits) - 1;
+        bits &= bits - 1;
+        const int64_t row = (w0 + src) * 32 + bit;
+        if (row >= nrows) break;
+        const int64_t base = row * (int64_t)row_len;
+        for (int c = lane; c < row_len; c += 32) {
+          const float gg = g[base + c];
+          g[base + c] = 0.f;
+          if (kind == 1) {
+            const float a2 = acc[base + c] + gg * gg;
+            acc[base + c] = a2;
+            p[base + c] = p[base + c] - lr * gg / sqrtf(a2 + eps);
+          } else {
+            p[base + c] = p[base + c] - lr * gg;
+          }
+        }
+      }
+    }
+    if (wi < nwords && word != 0u) touched[wi] = 0u;
+  }
+}
+
+__global__ void __launch_bounds__(256) dense_sgd_adagrad_kernel(float* __restrict__ p, float* __restrict__ acc,
+                                                                const float* __restrict__ g, int64_t n, float lr,
+                                                                float eps, int kind) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gg = g[i];
+    if (kind == 1) {
+      const float a2 = acc[i] + gg * gg;
+      acc[i] = a2;
+      p[i] = p[i] - lr * gg / sqrtf(a2 + eps);
+    } else {
+      p[i] = p[i] - lr * gg;
+    }
+  }
+}
+
+}  // namespace
+}  // namespace krs
+
+using namespace krs;
+
+extern "C" int krs_adamw(float* p, float* m, float* v, float* g, uint32_t* touched, int64_t n, int row_len, float lr,
+                         float b1, float b2, float eps, float wd, int64_t step, void* stream) {
+  KRS_REQUIRE(p && m && v && g, "krs_adamw: null argument");
+  KRS_REQUIRE(n >= 0 && step >= 1, "krs_adamw: bad n/step");
+  KRS_REQUIRE(touched == nullptr || (row_len > 0 && n % row_len == 0), "krs_adamw: arena needs n %% row_len == 0");
+  if (n == 0) return KRS_OK;
+  cudaStream_t s = as_stream(stream);
+  AdamArgs a;
+  a.lr = lr; a.b1 = b1; a.b2 = b2; a.eps = eps; a.wd = wd;
+  a.alpha = (float)((double)lr * sqrt(1.0 - pow((double)b2, (double)step)) / (1.0 - pow((double)b1, (double)step)));
+  const bool vec = (n % 4 == 0) && aligned16(p) && aligned16(m) && aligned16(v) && aligned16(g) &&
+                   (touched == nullptr || row_len % 4 == 0);
+  const int64_t work = vec ? n / 4 : n;
+  const unsigned grid = (unsigned)krs::imax<int64_t>(1, krs::imin<int64_t>(ceil_div<int64_t>(work, 256), (int64_t)sm_count() * 32));
+  if (vec) {
+    if (touched) adamw_vec_kernel<true><<<grid, 256, 0, s>>>(p, m, v, g, touched, work, row_len / 4, a);
+    else adamw_vec_kernel<false><<<grid, 256, 0, s>>>(p, m, v, g, nullptr, work, 1, a);
+  } else {
+    if (touched) adamw_scalar_kernel<true><<<grid, 256, 0, s>>>(p, m, v, g, touched, n, row_len, a);
+    else adamw_scalar_kernel<false><<<grid, 256, 0, s>>>(p, m, v, g, nullptr, n, 1, a);
+  }
+  KRS_LAUNCH_CHECK();
+  if (touched) {
+    const int64_t rows = n / row_len;
+    KRS_CUDA(cudaMemsetAsync(touched, 0, sizeof(uint32_t) * (size_t)ceil_div<int64_t>(rows, 32), s));
+  }
+  return KRS_OK;
+}
+
+extern "C" int krs_sgd_adagrad(float* p, float* acc, float* g, uint32_t* touched, int64_t n, int row_len, float lr,
+                               float eps, int kind, void* stream) {
+  KRS_REQUIRE(p && g, "krs_sgd_adagrad: null argument");
+  KRS_REQUIRE(kind == 0 || (kind == 1 && acc != nullptr), "krs_sgd_adagrad: kind must be 0 (SGD) or 1 (Adagrad + acc)");
+  KRS_REQUIRE(touched == nullptr || (row_len > 0 && n % row_len == 0), "krs_sgd_adagrad: arena needs n %% row_len == 0");
+  if (n == 0) return KRS_OK;
+  cudaStream_t s = as_stream(stream);
+  if (touched) {
+    const int64_t rows = n / row_len;
+    const int64_t nwords = ceil_div<int64_t>(rows, 32);
+    const unsigned grid =
+        (unsigned)krs::imax<int64_t>(1, krs::imin<int64_t>(ceil_div<int64_t>(ceil_div<int64_t>(nwords, 32), 8), (int64_t)sm_count() * 16));
+    sparse_rows_kernel<<<grid, 256, 0, s>>>(p, acc, g, touched, nwords, rows, row_len, lr, eps, kind);
+  } else {
+    const unsigned grid = (unsigned)krs::imax<int64_t>(1, krs::imin<int64_t>(ceil_div<int64_t>(n, 256), (int64_t)sm_count() * 32));
+    dense_sgd_adagrad_kernel<<<grid, 256, 0, s>>>(p, acc, g, n, lr, eps, kind);
+  }
+  KRS_LAUNCH_CHECK();
+  return KRS_OK;
+}

@@ -1,0 +1,12 @@
+"""keras_rs_b200.layers — same public names as keras_rs.layers (keras_rs/api/layers/__init__.py:7-36)
+for the hot path, plus the Keras core layers that path composes (Dense, Embedding)."""
+from .base import Layer, deserialize, serialize
+from .dense import Dense
+from .distributed_embedding import DistributedEmbedding, FeatureConfig, TableConfig
+from .dot_interaction import DotInteraction
+from .embedding import EmbedReduce, Embedding
+from .feature_cross import FeatureCross
+from .retrieval import BruteForceRetrieval, Retrieval
+
+__all__ = ["Layer", "Dense", "Embedding", "EmbedReduce", "DistributedEmbedding", "TableConfig", "FeatureConfig",
+           "FeatureCross", "DotInteraction", "Retrieval", "BruteForceRetrieval", "serialize", "deserialize"]
