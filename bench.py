@@ -214,7 +214,7 @@ def run_ours(a):
     kern = {}
     base = model.local if hasattr(model, "local") else model
     if world == 1:
-        bufs = base._buffers(B)
+        bufs = base._step_buffers(B)
         plan = bufs["plan"]
         out = bufs["xs"][0]
         s = stream()

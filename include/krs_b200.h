@@ -42,6 +42,9 @@ int krs_device_sm_count(void);         /* SMs of the current device (148 on B200
  * 1 = tcgen05 3xTF32 split (tensor pipe, fp32-level accuracy).  Process-wide default. */
 int krs_set_gemm_engine(int engine);
 int krs_get_gemm_engine(void);
+/* Number of tcgen05 GEMM launches so far in this process (tests use it to prove the tensor-pipe
+ * kernel, not the FFMA fallback, produced a result). */
+long long krs_gemm_tc_launch_count(void);
 
 /* ------------------------------------------------------------------ activations
  * keras.activations used as FeatureCross.pre_activation / Dense.activation

@@ -315,7 +315,7 @@ int fill_params(GatherParams& p, const krs_feature_t* features, int F, int64_t B
   KRS_REQUIRE(B >= 0, "gather: negative batch");
   for (int i = 0; i < F; ++i) {
     const krs_feature_t& f = features[i];
-    KRS_REQUIRE(f.ids != nullptr, "gather: feature %d has null ids", i);
+    KRS_REQUIRE(f.ids != nullptr || B == 0, "gather: feature %d has null ids", i);
     KRS_REQUIRE(f.dim > 0 && f.hotness > 0 && f.vocab > 0, "gather: feature %d has bad dim/hotness/vocab", i);
     KRS_REQUIRE(f.combiner >= 0 && f.combiner <= 2, "gather: feature %d has unknown combiner %d", i, f.combiner);
     KRS_REQUIRE(f.out_offset >= 0 && f.out_offset + f.dim <= out_ld, "gather: feature %d columns exceed out_ld", i);

@@ -1,9 +1,500 @@
-// gemm_tc.cu — tcgen05 3xTF32 GEMM (placeholder until the UMMA kernel lands: reports unsupported so
-// krs::gemm falls through to the exact FFMA engine).
+// gemm_tc.cu — tcgen05 (5th-gen tensor core) GEMM with fp32-level accuracy via a 3-term TF32 split.
+//
+// "Engine 1" of krs::gemm: the dense contractions of FeatureCross / Dense and their backward passes
+// (W·x_i, dz·V^T, x^T·dz) on the tensor pipe, with the same fused epilogues as gemm_ffma.cu
+// (+bias, pre_activation, +diag·x, x0 ⊙ (·) + x kept in registers).
+//
+// Accuracy: inputs are fp32.  Each operand is split in-kernel into hi = tf32(x) and
+// lo = tf32(x - hi); the product is accumulated as lo·hi + hi·lo + hi·hi in fp32 TMEM accumulators
+// (the dropped lo·lo term is ~2^-22 relative), which keeps results within ~1e-6 of an fp32 matmul —
+// inside the 1e-5 bar of the north star, which a single-pass TF32 product (1e-3) would miss.
+//
+// Structure (one CTA per SM, persistent over output tiles, 320 threads):
+//   warp 0      TMA producer: cp.async.bulk.tensor fp32 tiles global -> shared (mbarrier complete_tx)
+//   warp 1      MMA issuer: one elected lane issues tcgen05.mma.kind::tf32 (SS operands, D in TMEM),
+//               tcgen05.commit releases shared-memory stages / publishes the accumulator
+//   warps 2-5   converters: shared -> registers -> shared, write hi (in place) and lo tiles
+//   warps 6-9   epilogue: tcgen05.ld accumulator rows -> registers -> fused epilogue -> global
+// Shared memory ring: 4 stages x (A_raw | B_raw | A_lo | B_lo), BK = 16 floats per stage.
+// TMEM: 512 columns = 2 accumulator stages x 256 columns (128 lanes = the 128 rows of the tile).
+//
+// Operand layouts: K-contiguous operands use 64-byte rows with SWIZZLE_64B (K-major UMMA
+// descriptors), MN-contiguous operands (x^T, dz in the weight-gradient GEMM, V in the forward) use
+// 32-element x 16-row boxes with SWIZZLE_128B (MN-major descriptors).  Ragged edges are handled by
+// TMA out-of-bounds zero fill on loads and guards on stores.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <atomic>
+#include <mutex>
+
 #include "common.cuh"
+
 namespace krs {
-int gemm_tc(const float*, int64_t, bool, const float*, int64_t, bool, float*, int64_t, int64_t, int64_t, int64_t,
-            const Epilogue&, int, bool, cudaStream_t) {
-  return KRS_EUNSUPPORTED;
+namespace {
+
+constexpr int BM = 128;          // rows per tile == TMEM lanes
+constexpr int BK = 16;           // fp32 elements per k-block (64 B)
+constexpr int STAGES = 4;
+constexpr int MAX_BN = 256;
+constexpr int NUM_THREADS = 320;
+constexpr int A_BYTES = BM * BK * 4;             // 8192
+constexpr int SPIN_LIMIT = 1 << 26;              // turns a protocol bug into a trap instead of a hang
+
+std::atomic<long long> g_tc_launches{0};
+
+struct TcArgs {
+  float* C;
+  int64_t ldc;
+  int64_t M, N, K;
+  int bn;                 // N tile (multiple of 16, <= 256)
+  int tiles_m, tiles_n, splits;
+  int64_t kblocks_total;  // ceil(K / BK)
+  int64_t kblocks_per_split;
+  int a_mn_major, b_mn_major;
+  int atomic_out, accumulate;
+  Epilogue epi;
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok = 0;
+  int spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) break;
+    if (++spins > SPIN_LIMIT) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor; version = 1 on sm_100).
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;                    // version
+  d |= (uint64_t)(layout_type & 7) << 61;    // 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
+  return d;
+}
+// K-major tile: rows of 64 B (BK floats), SWIZZLE_64B, 8-row groups 512 B apart; k-step = +32 B.
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile_addr, int kstep) {
+  return make_desc(tile_addr + kstep * 32, 16, 512, 4);
+}
+// MN-major tile: blocks of 32 mn x 16 k (2048 B, SWIZZLE_128B); 8-k groups 1024 B apart (SBO),
+// mn blocks 2048 B apart (LBO); k-step = +1024 B.
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile_addr, int kstep) {
+  return make_desc(tile_addr + kstep * 1024, 2048, 1024, 2);
+}
+
+__device__ __forceinline__ float tf32_rna_f(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// ---------------------------------------------------------------- fused epilogue on 16 columns of one row
+__device__ __forceinline__ void epilogue_row16(const TcArgs& g, int64_t m, int64_t n0, const uint32_t (&acc)[16]) {
+  const Epilogue& e = g.epi;
+  const int64_t off = m * g.ldc + n0;
+  const int cnt = (int)imin<int64_t>(16, g.N - n0);
+  if (cnt <= 0) return;
+  if (g.atomic_out) {
+    for (int j = 0; j < cnt; ++j) atomicAdd(g.C + off + j, __uint_as_float(acc[j]));
+    return;
+  }
+  const bool vec = (cnt == 16) && ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15u) == 0) && ((n0 & 3) == 0);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float v[4], out[4], h2v[4], zv[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = __uint_as_float(acc[q * 4 + j]);
+    const int64_t o = off + q * 4;
+    const int64_t n = n0 + q * 4;
+    const int c4 = vec ? 4 : (int)imax<int64_t>(0, imin<int64_t>(4, g.N - n));
+    if (c4 <= 0) break;
+    if (e.kind == EPI_NONE) {
+      for (int j = 0; j < c4; ++j) out[j] = v[j] + (g.accumulate ? g.C[o + j] : 0.f);
+    } else if (e.kind == EPI_BIAS_ACT) {
+      for (int j = 0; j < c4; ++j) out[j] = act_apply(e.act, v[j] + (e.bias ? e.bias[n + j] : 0.f));
+    } else if (e.kind == EPI_CROSS) {
+      float x0v[4], xv[4];
+      if (vec) {
+        const float4 a = *reinterpret_cast<const float4*>(e.x0 + o);
+        const float4 b = *reinterpret_cast<const float4*>(e.x + o);
+        x0v[0] = a.x; x0v[1] = a.y; x0v[2] = a.z; x0v[3] = a.w;
+        xv[0] = b.x; xv[1] = b.y; xv[2] = b.z; xv[3] = b.w;
+      } else {
+        for (int j = 0; j < c4; ++j) { x0v[j] = e.x0[o + j]; xv[j] = e.x[o + j]; }
+      }
+      for (int j = 0; j < c4; ++j) {
+        const float z = v[j] + (e.bias ? e.bias[n + j] : 0.f);
+        const float a = act_apply(e.act, z);
+        const float h2 = (e.diag != 0.f) ? a + e.diag * xv[j] : a;
+        zv[j] = z;
+        h2v[j] = h2;
+        out[j] = x0v[j] * h2 + xv[j];
+      }
+      if (e.h2_out) {
+        if (vec) *reinterpret_cast<float4*>(e.h2_out + o) = make_float4(h2v[0], h2v[1], h2v[2], h2v[3]);
+        else for (int j = 0; j < c4; ++j) e.h2_out[o + j] = h2v[j];
+      }
+      if (e.z_out) {
+        if (vec) *reinterpret_cast<float4*>(e.z_out + o) = make_float4(zv[0], zv[1], zv[2], zv[3]);
+        else for (int j = 0; j < c4; ++j) e.z_out[o + j] = zv[j];
+      }
+    } else {  // EPI_ADD2
+      for (int j = 0; j < c4; ++j) {
+        float r = v[j];
+        if (e.add1) r += e.alpha1 * e.add1[o + j];
+        if (e.add2) r += e.alpha2 * e.add2[o + j];
+        out[j] = r;
+      }
+    }
+    if (vec) *reinterpret_cast<float4*>(g.C + o) = make_float4(out[0], out[1], out[2], out[3]);
+    else for (int j = 0; j < c4; ++j) g.C[o + j] = out[j];
+  }
+}
+
+// ---------------------------------------------------------------- the kernel
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const TcArgs g) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  // carve: stages first (1024-aligned), then barriers
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int b_bytes = g.bn * BK * 4;
+  const int raw_bytes = A_BYTES + b_bytes;
+  const int stage_bytes = 2 * raw_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * stage_bytes);
+  uint64_t* full_bar = bars;                 // [STAGES] TMA landed
+  uint64_t* conv_bar = bars + STAGES;        // [STAGES] hi/lo tiles ready
+  uint64_t* empty_bar = bars + 2 * STAGES;   // [STAGES] MMAs that read the stage have completed
+  uint64_t* tmem_full = bars + 3 * STAGES;   // [2]
+  uint64_t* tmem_empty = bars + 3 * STAGES + 2;  // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&conv_bar[s], 4);      // one arrival per converter warp
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 4);    // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int64_t tiles_mn = (int64_t)g.tiles_m * g.tiles_n;
+  const int64_t total_tiles = tiles_mn * g.splits;
+
+  if (warp == 0) {
+    // ======================= TMA producer =======================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int split = (int)(tile / tiles_mn);
+        const int64_t rem = tile - (int64_t)split * tiles_mn;
+        const int tn = (int)(rem / g.tiles_m);
+        const int tm = (int)(rem - (int64_t)tn * g.tiles_m);
+        const int64_t kb0 = (int64_t)split * g.kblocks_per_split;
+        const int64_t kb1 = imin<int64_t>(g.kblocks_total, kb0 + g.kblocks_per_split);
+        for (int64_t kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          unsigned char* st = smem + (size_t)stage * stage_bytes;
+          mbar_expect_tx(&full_bar[stage], (uint32_t)raw_bytes);
+          const int k0 = (int)(kb * BK);
+          if (!g.a_mn_major) {
+            tma_load_2d(st, &tmap_a, k0, tm * BM, &full_bar[stage]);                  // box {16 k, 128 m}
+          } else {
+            for (int blk = 0; blk < BM / 32; ++blk)
+              tma_load_2d(st + blk * 2048, &tmap_a, tm * BM + blk * 32, k0, &full_bar[stage]);   // box {32 m, 16 k}
+          }
+          unsigned char* sb = st + A_BYTES;
+          if (!g.b_mn_major) {
+            tma_load_2d(sb, &tmap_b, k0, tn * g.bn, &full_bar[stage]);                // box {16 k, bn n}
+          } else {
+            for (int blk = 0; blk < g.bn / 32; ++blk)
+              tma_load_2d(sb + blk * 2048, &tmap_b, tn * g.bn + blk * 32, k0, &full_bar[stage]);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer =======================
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)g.a_mn_major << 15) |
+                           ((uint32_t)g.b_mn_major << 16) | ((uint32_t)(g.bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int split = (int)(tile / tiles_mn);
+      const int64_t kb0 = (int64_t)split * g.kblocks_per_split;
+      const int64_t kb1 = imin<int64_t>(g.kblocks_total, kb0 + g.kblocks_per_split);
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * MAX_BN);
+      for (int64_t kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&conv_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_hi = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint32_t b_hi = a_hi + A_BYTES;
+          const uint32_t a_lo = a_hi + raw_bytes;
+          const uint32_t b_lo = b_hi + raw_bytes;
+#pragma unroll
+          for (int ks = 0; ks < BK / 8; ++ks) {
+            const uint64_t dah = g.a_mn_major ? desc_mnmajor(a_hi, ks) : desc_kmajor(a_hi, ks);
+            const uint64_t dal = g.a_mn_major ? desc_mnmajor(a_lo, ks) : desc_kmajor(a_lo, ks);
+            const uint64_t dbh = g.b_mn_major ? desc_mnmajor(b_hi, ks) : desc_kmajor(b_hi, ks);
+            const uint64_t dbl = g.b_mn_major ? desc_mnmajor(b_lo, ks) : desc_kmajor(b_lo, ks);
+            const uint32_t first = (kb == kb0 && ks == 0) ? 0u : 1u;
+            tc_mma_tf32(d_tmem, dal, dbh, idesc, first);     // small terms first
+            tc_mma_tf32(d_tmem, dah, dbl, idesc, 1u);
+            tc_mma_tf32(d_tmem, dah, dbh, idesc, 1u);
+          }
+          tc_commit(&empty_bar[stage]);                       // frees the stage when these MMAs retire
+          if (kb == kb1 - 1) tc_commit(&tmem_full[acc]);      // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (kb1 <= kb0 && lane == 0) tc_commit(&tmem_full[acc]);   // empty K range (K == 0): nothing accumulated
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp < 6) {
+    // ======================= converters (128 threads) =======================
+    const int ct = threadIdx.x - 64;        // 0..127
+    int stage = 0;
+    uint32_t phase = 0;
+    const int nvec = raw_bytes / 16;
+    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int split = (int)(tile / tiles_mn);
+      const int64_t kb0 = (int64_t)split * g.kblocks_per_split;
+      const int64_t kb1 = imin<int64_t>(g.kblocks_total, kb0 + g.kblocks_per_split);
+      for (int64_t kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        float4* raw = reinterpret_cast<float4*>(smem + (size_t)stage * stage_bytes);
+        float4* lo = reinterpret_cast<float4*>(smem + (size_t)stage * stage_bytes + raw_bytes);
+        for (int i = ct; i < nvec; i += 128) {
+          const float4 x = raw[i];
+          float4 h, l;
+          h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+          h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+          h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+          h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+          l.x = tf32_rna_f(x.x - h.x);
+          l.y = tf32_rna_f(x.y - h.y);
+          l.z = tf32_rna_f(x.z - h.z);
+          l.w = tf32_rna_f(x.w - h.w);
+          raw[i] = h;
+          lo[i] = l;
+        }
+        // generic-proxy writes must be visible to the tensor core (async proxy) before the MMA reads them
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&conv_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ======================= epilogue (warps 6..9) =======================
+    const int quad = warp & 3;              // TMEM lane quadrant this warp may read
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int split = (int)(tile / tiles_mn);
+      const int64_t rem = tile - (int64_t)split * tiles_mn;
+      const int tn = (int)(rem / g.tiles_m);
+      const int tm = (int)(rem - (int64_t)tn * g.tiles_m);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int64_t m = (int64_t)tm * BM + quad * 32 + lane;
+      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * MAX_BN);
+      const bool empty_k = ((int64_t)split * g.kblocks_per_split) >= g.kblocks_total;
+      for (int c = 0; c < g.bn; c += 16) {
+        uint32_t r[16];
+        tc_ld16(t_row + (uint32_t)c, r);
+        tc_wait_ld();
+        if (empty_k) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) r[j] = 0u;
+        }
+        const int64_t n0 = (int64_t)tn * g.bn + c;
+        if (m < g.M && n0 < g.N) epilogue_row16(g, m, n0, r);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+  }
+}
+
+// ---------------------------------------------------------------- host side
+PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+// Row-major matrix [rows][cols] (cols contiguous, leading dimension ld).  box = {box_cols, box_rows}.
+bool make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows,
+              CUtensorMapSwizzle swz) {
+  auto fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+int pick_bn(int64_t N, bool b_mn_major) {
+  const int gran = b_mn_major ? 32 : 16;
+  const int64_t tiles = ceil_div<int64_t>(N, MAX_BN);
+  int64_t bn = ceil_div<int64_t>(ceil_div<int64_t>(N, tiles), gran) * gran;
+  if (bn > MAX_BN) bn = MAX_BN;
+  if (bn < gran) bn = gran;
+  return (int)bn;
+}
+
+}  // namespace
+
+long long gemm_tc_launches() { return g_tc_launches.load(); }
+
+int gemm_tc(const float* A, int64_t lda, bool transA, const float* B, int64_t ldb, bool transB, float* C, int64_t ldc,
+            int64_t M, int64_t N, int64_t K, const Epilogue& epi, int split_k, bool accumulate, cudaStream_t stream) {
+  // shapes the tensor-core path does not cover fall back to the exact FFMA engine
+  if (M < 64 || N < 16 || K < 16) return KRS_EUNSUPPORTED;
+  if (!aligned16(A) || !aligned16(B) || (lda % 4) != 0 || (ldb % 4) != 0) return KRS_EUNSUPPORTED;
+  if (M >= ((int64_t)1 << 31) || N >= ((int64_t)1 << 31) || K >= ((int64_t)1 << 31)) return KRS_EUNSUPPORTED;
+  if (split_k < 1) split_k = 1;
+  KRS_REQUIRE(split_k == 1 || epi.kind == EPI_NONE, "gemm_tc: split-K only with the plain epilogue");
+  if (encode_fn() == nullptr) return KRS_EUNSUPPORTED;
+
+  TcArgs g;
+  g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K;
+  g.a_mn_major = transA ? 1 : 0;       // A stored (K,M): M contiguous
+  g.b_mn_major = transB ? 0 : 1;       // B stored (K,N): N contiguous ; transB: stored (N,K): K contiguous
+  g.bn = pick_bn(N, g.b_mn_major != 0);
+  g.tiles_m = (int)ceil_div<int64_t>(M, BM);
+  g.tiles_n = (int)ceil_div<int64_t>(N, g.bn);
+  g.kblocks_total = ceil_div<int64_t>(K, BK);
+  g.kblocks_per_split = ceil_div<int64_t>(g.kblocks_total, split_k);
+  g.splits = (int)ceil_div<int64_t>(g.kblocks_total, g.kblocks_per_split);
+  g.atomic_out = g.splits > 1 ? 1 : 0;
+  g.accumulate = accumulate ? 1 : 0;
+  g.epi = epi;
+
+  CUtensorMap ma, mb;
+  bool ok;
+  if (!g.a_mn_major) ok = make_map(&ma, A, M, K, lda, BK, BM, CU_TENSOR_MAP_SWIZZLE_64B);        // [M][K]
+  else ok = make_map(&ma, A, K, M, lda, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B);                     // [K][M]
+  if (!ok) return KRS_EUNSUPPORTED;
+  if (!g.b_mn_major) ok = make_map(&mb, B, N, K, ldb, BK, g.bn, CU_TENSOR_MAP_SWIZZLE_64B);      // [N][K]
+  else ok = make_map(&mb, B, K, N, ldb, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B);                     // [K][N]
+  if (!ok) return KRS_EUNSUPPORTED;
+
+  if (g.atomic_out && !accumulate)
+    KRS_CUDA(cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, stream));
+
+  const size_t stage_bytes = 2 * (size_t)(A_BYTES + g.bn * BK * 4);
+  const size_t smem = 1024 + STAGES * stage_bytes + 256;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  });
+  KRS_CUDA(attr_err);
+  const int64_t total_tiles = (int64_t)g.tiles_m * g.tiles_n * g.splits;
+  const unsigned grid = (unsigned)imax<int64_t>(1, imin<int64_t>(total_tiles, sm_count()));
+  gemm_tc_kernel<<<grid, NUM_THREADS, smem, stream>>>(ma, mb, g);
+  KRS_LAUNCH_CHECK();
+  g_tc_launches.fetch_add(1);
+  return KRS_OK;
+}
+
 }  // namespace krs
+
+extern "C" long long krs_gemm_tc_launch_count(void) { return krs::gemm_tc_launches(); }

@@ -156,7 +156,7 @@ class DCN(torch.nn.Module):
         return h
 
     # ------------------------------------------------------------------ fused training step
-    def _buffers(self, B: int):
+    def _step_buffers(self, B: int):
         b = self._bufs.get(B)
         if b is not None:
             return b
@@ -188,7 +188,7 @@ class DCN(torch.nn.Module):
         be pinned-host or device tensors; they are copied into the static device buffers (this IS the
         per-step host->device transfer).  Gradients land in emb_grad/emb_touched and dense_grad_flat."""
         B = ids.shape[0]
-        b = self._buffers(B)
+        b = self._step_buffers(B)
         b["ids"].copy_(ids, non_blocking=True)
         b["labels"].copy_(labels.reshape(-1), non_blocking=True)
         s = stream()

@@ -39,11 +39,12 @@ class FeatureCross(Layer):
 
     def build(self, input_shape, *unused) -> None:
         last_dim = int(input_shape[-1])                                 # :131
-        self.down_proj_kernel = None
         if self.projection_dim is not None:                            # :133-140 (no bias, no activation)
             self.down_proj_kernel = self.add_weight(
                 "down_proj_kernel", (last_dim, int(self.projection_dim)),
                 initializers.clone_initializer(self.kernel_initializer))
+        else:
+            self.down_proj_kernel = None
         k_in = last_dim if self.projection_dim is None else int(self.projection_dim)
         self.kernel = self.add_weight("kernel", (k_in, last_dim), initializers.clone_initializer(self.kernel_initializer))
         self.bias = (self.add_weight("bias", (last_dim,), initializers.clone_initializer(self.bias_initializer))
