@@ -82,6 +82,7 @@ typedef struct krs_feature {
   /* local row r/S (tensorflow/distributed_embedding.py:316-328).  `table` is ignored.           */
   const float* const* shard_tables;
   float* const* shard_grads;
+  uint32_t* const* shard_touched; /* bwd only, nullable: per-shard bitmaps indexed by LOCAL row     */
   int32_t num_shards;
   int32_t _pad;
 } krs_feature_t;

@@ -35,7 +35,8 @@ class KrsFeature(C.Structure):
         ("touched", C.c_void_p), ("vocab", C.c_int64), ("ids_stride", C.c_int64),
         ("hotness", C.c_int32), ("dim", C.c_int32), ("out_offset", C.c_int32),
         ("combiner", C.c_int32), ("ids_i64", C.c_int32), ("reduce", C.c_int32),
-        ("shard_tables", C.c_void_p), ("shard_grads", C.c_void_p), ("num_shards", C.c_int32),
+        ("shard_tables", C.c_void_p), ("shard_grads", C.c_void_p), ("shard_touched", C.c_void_p),
+        ("num_shards", C.c_int32),
         ("_pad", C.c_int32),
     ]
 

@@ -51,7 +51,7 @@ __device__ __forceinline__ const float* row_ptr(const krs_feature_t& f, int64_t 
 // ------------------------------------------------------------------ forward, fast path
 // Requirements (checked on the host): every feature 1-hot, no weights, same dim E = 4*LPR,
 // out_offset = f*E, out_ld = F*E, single shard.  Rows are numbered r = b*F + f.
-template <int LPR, int UNROLL, typename IdT>
+template <int LPR, int UNROLL, typename IdT, bool SHARDED>
 __global__ void __launch_bounds__(256) gather_fast_kernel(const __grid_constant__ GatherParams p) {
   constexpr int RPW = 32 / LPR;              // rows per warp per step
   constexpr int E = LPR * 4;
@@ -72,7 +72,12 @@ __global__ void __launch_bounds__(256) gather_fast_kernel(const __grid_constant_
         const int f = (int)(r - b * F);
         const krs_feature_t& ft = p.f[f];
         const int64_t id = clamp_id(load_id<IdT>(ft.ids, b * ft.ids_stride), ft.vocab);
-        src[u] = ft.table + id * E + sub * 4;
+        if (SHARDED) {
+          const int S = ft.num_shards;
+          src[u] = ft.shard_tables[(int)(id % S)] + (id / S) * E + sub * 4;   // peer-mapped shard: rows cross NVLink here
+        } else {
+          src[u] = ft.table + id * E + sub * 4;
+        }
       }
     }
     float4 v[UNROLL];
@@ -251,7 +256,16 @@ __global__ void __launch_bounds__(256) scatter_fast_kernel(const __grid_constant
     if (valid) id = clamp_id(load_id<IdT>(ft.ids, b * ft.ids_stride), ft.vocab);
     const unsigned peers = __match_any_sync(0xffffffffu, id);
     const bool leader = valid && ((__ffs(peers) - 1) == lane);
-    if (leader && ft.touched) atomicOr(ft.touched + (id >> 5), 1u << (id & 31));
+    if (leader) {
+      if (ft.num_shards > 1) {
+        if (ft.shard_touched) {
+          const int64_t lr = id / ft.num_shards;
+          atomicOr(ft.shard_touched[(int)(id % ft.num_shards)] + (lr >> 5), 1u << (lr & 31));
+        }
+      } else if (ft.touched) {
+        atomicOr(ft.touched + (id >> 5), 1u << (id & 31));
+      }
+    }
     const unsigned leaders = __ballot_sync(0xffffffffu, leader);
     const int E = ft.dim;
     for (unsigned m = leaders; m; m &= m - 1) {
@@ -304,7 +318,16 @@ __global__ void __launch_bounds__(256) scatter_generic_kernel(const __grid_const
       float* drow;
       if (ft.num_shards > 1) drow = ft.shard_grads[(int)(id % ft.num_shards)] + (id / ft.num_shards) * (int64_t)E;
       else drow = ft.grad + id * (int64_t)E;
-      if (lane == 0 && ft.touched) atomicOr(ft.touched + (id >> 5), 1u << (id & 31));
+      if (lane == 0) {
+        if (ft.num_shards > 1) {
+          if (ft.shard_touched) {
+            const int64_t lr = id / ft.num_shards;
+            atomicOr(ft.shard_touched[(int)(id % ft.num_shards)] + (lr >> 5), 1u << (lr & 31));
+          }
+        } else if (ft.touched) {
+          atomicOr(ft.touched + (id >> 5), 1u << (id & 31));
+        }
+      }
       for (int c = lane; c < E; c += 32) atomicAdd(drow + c, coef * g[c]);
     }
   }
@@ -330,23 +353,25 @@ int fill_params(GatherParams& p, const krs_feature_t* features, int F, int64_t B
   return KRS_OK;
 }
 
-bool uniform_onehot(const GatherParams& p, int* E_out, bool* i64) {
+bool uniform_onehot(const GatherParams& p, int* E_out, bool* i64, bool* sharded) {
   const int E = p.f[0].dim;
   const int is64 = p.f[0].ids_i64;
+  const bool sh = p.f[0].num_shards > 1;
   for (int i = 0; i < p.F; ++i) {
     const krs_feature_t& f = p.f[i];
-    if (f.hotness != 1 || f.dim != E || f.ids_i64 != is64 || f.num_shards > 1) return false;
+    if (f.hotness != 1 || f.dim != E || f.ids_i64 != is64 || ((f.num_shards > 1) != sh)) return false;
     if (f.weights != nullptr && (f.reduce || f.combiner == KRS_COMBINER_SUM)) return false;
     if (f.out_offset != i * E) return false;
-    if (f.table == nullptr || !aligned16(f.table)) return false;
+    if (!sh && (f.table == nullptr || !aligned16(f.table))) return false;
   }
+  *sharded = sh;
   if (p.out_ld != (int64_t)p.F * E || !aligned16(p.out)) return false;
   *E_out = E;
   *i64 = is64 != 0;
   return true;
 }
 
-template <int LPR, typename IdT>
+template <int LPR, typename IdT, bool SHARDED>
 int launch_fast(const GatherParams& p, cudaStream_t s) {
   constexpr int UNROLL = (LPR >= 16) ? 4 : 8;
   const int64_t R = p.B * p.F;
@@ -355,7 +380,7 @@ int launch_fast(const GatherParams& p, cudaStream_t s) {
   const int64_t blocks_needed = ceil_div<int64_t>(warps_needed, 8);
   const int64_t cap = (int64_t)sm_count() * 8 * 4;        // up to 4 grid-stride trips beyond full residency
   const unsigned grid = (unsigned)krs::imax<int64_t>(1, min(blocks_needed, cap));
-  gather_fast_kernel<LPR, UNROLL, IdT><<<grid, 256, 0, s>>>(p);
+  gather_fast_kernel<LPR, UNROLL, IdT, SHARDED><<<grid, 256, 0, s>>>(p);
   KRS_LAUNCH_CHECK();
   return KRS_OK;
 }
@@ -390,25 +415,32 @@ extern "C" int krs_gather_fwd(const krs_feature_t* features, int F, int64_t B, f
   GatherParams p;
   int rc = fill_params(p, features, F, B, out, out_ld);
   if (rc) return rc;
-  KRS_REQUIRE(out != nullptr, "krs_gather_fwd: null output");
+  KRS_REQUIRE(out != nullptr || B == 0, "krs_gather_fwd: null output");
   for (int i = 0; i < F; ++i)
     KRS_REQUIRE(p.f[i].num_shards > 1 ? p.f[i].shard_tables != nullptr : p.f[i].table != nullptr,
                 "krs_gather_fwd: feature %d has no table", i);
   if (B == 0) return KRS_OK;
   cudaStream_t s = as_stream(stream);
   int E = 0;
-  bool i64 = false;
-  const bool fast_ok = uniform_onehot(p, &E, &i64) && (E % 4 == 0) && ((E / 4) & (E / 4 - 1)) == 0 && E <= 128;
+  bool i64 = false, sharded = false;
+  const bool fast_ok = uniform_onehot(p, &E, &i64, &sharded) && (E % 4 == 0) && ((E / 4) & (E / 4 - 1)) == 0 && E <= 128;
   KRS_REQUIRE(variant >= 0 && variant <= 3, "krs_gather_fwd: unknown variant %d", variant);
   if ((variant == 1 || variant == 2) && !fast_ok) {
     set_error("krs_gather_fwd: variant %d needs 1-hot features of one dim E in {4,8,16,32,64,128}", variant);
     return KRS_EUNSUPPORTED;
   }
-  if (variant == 2) return i64 ? launch_bulk<int64_t>(p, E, s) : launch_bulk<int32_t>(p, E, s);
+  if (variant == 2) {
+    if (sharded) {
+      set_error("krs_gather_fwd: the bulk-copy variant does not address sharded tables");
+      return KRS_EUNSUPPORTED;
+    }
+    return i64 ? launch_bulk<int64_t>(p, E, s) : launch_bulk<int32_t>(p, E, s);
+  }
   if (fast_ok && variant != 3) {
 #define KRS_FAST(L)                                                              \
   case L:                                                                        \
-    return i64 ? launch_fast<L, int64_t>(p, s) : launch_fast<L, int32_t>(p, s);
+    if (sharded) return i64 ? launch_fast<L, int64_t, true>(p, s) : launch_fast<L, int32_t, true>(p, s); \
+    return i64 ? launch_fast<L, int64_t, false>(p, s) : launch_fast<L, int32_t, false>(p, s);
     switch (E / 4) {
       KRS_FAST(1)
       KRS_FAST(2)
@@ -458,7 +490,7 @@ extern "C" int krs_gather_bwd(const krs_feature_t* features, int F, int64_t B, c
   cudaStream_t s = as_stream(stream);
   if (fast) {
     const int64_t items = ceil_div<int64_t>(B, 32) * F;
-    const unsigned grid = (unsigned)krs::imax<int64_t>(1, krs::imin<int64_t>(ceil_div<int64_t>(items, 8), (int64_t)sm_count() * 16));
+    const unsigned grid = (unsigned)krs::imax<int64_t>(1, krs::imin<int64_t>(ceil_div<int64_t>(items, 8), 0x7fffffff));
     if (is64) scatter_fast_kernel<int64_t><<<grid, 256, 0, s>>>(p);
     else scatter_fast_kernel<int32_t><<<grid, 256, 0, s>>>(p);
   } else {

@@ -25,6 +25,8 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
+#include <stdlib.h>
+
 #include <atomic>
 #include <mutex>
 
@@ -53,6 +55,7 @@ struct TcArgs {
   int64_t kblocks_per_split;
   int a_mn_major, b_mn_major;
   int atomic_out, accumulate;
+  int mn_lbo, mn_sbo, mn_kstep;   // MN-major descriptor strides (bytes)
   Epilogue epi;
 };
 
@@ -133,8 +136,8 @@ __device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile_addr, int kstep) {
 }
 // MN-major tile: blocks of 32 mn x 16 k (2048 B, SWIZZLE_128B); 8-k groups 1024 B apart (SBO),
 // mn blocks 2048 B apart (LBO); k-step = +1024 B.
-__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile_addr, int kstep) {
-  return make_desc(tile_addr + kstep * 1024, 2048, 1024, 2);
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile_addr, int kstep, const TcArgs& g) {
+  return make_desc(tile_addr + kstep * g.mn_kstep, g.mn_lbo, g.mn_sbo, 2);
 }
 
 __device__ __forceinline__ float tf32_rna_f(float x) {
@@ -309,10 +312,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const uint32_t b_lo = b_hi + raw_bytes;
 #pragma unroll
           for (int ks = 0; ks < BK / 8; ++ks) {
-            const uint64_t dah = g.a_mn_major ? desc_mnmajor(a_hi, ks) : desc_kmajor(a_hi, ks);
-            const uint64_t dal = g.a_mn_major ? desc_mnmajor(a_lo, ks) : desc_kmajor(a_lo, ks);
-            const uint64_t dbh = g.b_mn_major ? desc_mnmajor(b_hi, ks) : desc_kmajor(b_hi, ks);
-            const uint64_t dbl = g.b_mn_major ? desc_mnmajor(b_lo, ks) : desc_kmajor(b_lo, ks);
+            const uint64_t dah = g.a_mn_major ? desc_mnmajor(a_hi, ks, g) : desc_kmajor(a_hi, ks);
+            const uint64_t dal = g.a_mn_major ? desc_mnmajor(a_lo, ks, g) : desc_kmajor(a_lo, ks);
+            const uint64_t dbh = g.b_mn_major ? desc_mnmajor(b_hi, ks, g) : desc_kmajor(b_hi, ks);
+            const uint64_t dbl = g.b_mn_major ? desc_mnmajor(b_lo, ks, g) : desc_kmajor(b_lo, ks);
             const uint32_t first = (kb == kb0 && ks == 0) ? 0u : 1u;
             tc_mma_tf32(d_tmem, dal, dbh, idesc, first);     // small terms first
             tc_mma_tf32(d_tmem, dah, dbl, idesc, 1u);
@@ -466,6 +469,10 @@ int gemm_tc(const float* A, int64_t lda, bool transA, const float* B, int64_t ld
   g.atomic_out = g.splits > 1 ? 1 : 0;
   g.accumulate = accumulate ? 1 : 0;
   g.epi = epi;
+  g.mn_lbo = 2048; g.mn_sbo = 1024; g.mn_kstep = 1024;
+  if (const char* e = getenv("KRS_TC_MN_LBO")) g.mn_lbo = atoi(e);       // debug overrides
+  if (const char* e = getenv("KRS_TC_MN_SBO")) g.mn_sbo = atoi(e);
+  if (const char* e = getenv("KRS_TC_MN_KSTEP")) g.mn_kstep = atoi(e);
 
   CUtensorMap ma, mb;
   bool ok;

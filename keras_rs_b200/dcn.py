@@ -47,27 +47,7 @@ class DCN(torch.nn.Module):
         self.device_ = torch.device(device)
         self.world = 1
         self.rank = 0
-        # ---- embedding arena -------------------------------------------------
-        self.row_off = []
-        off = 0
-        for v in self.vocab_sizes:
-            self.row_off.append(off)
-            off += _round_up(v, 32)
-        self.total_rows = off
-        g = torch.Generator(device="cpu").manual_seed(seed)
-        init = initializers.get(embeddings_initializer)
-        emb = torch.zeros((self.total_rows, self.E), dtype=torch.float32)
-        for f, v in enumerate(self.vocab_sizes):
-            if isinstance(init, initializers.RandomUniform):
-                emb[self.row_off[f]:self.row_off[f] + v] = (
-                    torch.rand((v, self.E), generator=g) * (init.maxval - init.minval) + init.minval)
-            else:
-                emb[self.row_off[f]:self.row_off[f] + v] = init((v, self.E))
-        self.emb = torch.nn.Parameter(emb.to(self.device_))
-        self.emb_grad = torch.zeros_like(self.emb)                      # gradient arena (persistently zero)
-        self.emb_touched = torch.zeros((self.total_rows // 32,), dtype=torch.int32, device=self.device_)
-        self.emb._krs_arena = self.emb_grad
-        self.emb._krs_touched = self.emb_touched
+        self._init_tables(seed, embeddings_initializer)
         # ---- cross + MLP layers (public layer classes) --------------------------
         self.cross = torch.nn.ModuleList([
             FeatureCross(projection_dim=projection_dim, diag_scale=diag_scale, pre_activation=pre_activation,
@@ -90,6 +70,28 @@ class DCN(torch.nn.Module):
         self._bufs = {}
         self._plan = None
         self._plan_key = None
+
+    def _init_tables(self, seed, embeddings_initializer):
+        self.row_off = []
+        off = 0
+        for v in self.vocab_sizes:
+            self.row_off.append(off)
+            off += _round_up(v, 32)
+        self.total_rows = off
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        init = initializers.get(embeddings_initializer)
+        emb = torch.zeros((self.total_rows, self.E), dtype=torch.float32)
+        for f, v in enumerate(self.vocab_sizes):
+            if isinstance(init, initializers.RandomUniform):
+                emb[self.row_off[f]:self.row_off[f] + v] = (
+                    torch.rand((v, self.E), generator=g) * (init.maxval - init.minval) + init.minval)
+            else:
+                emb[self.row_off[f]:self.row_off[f] + v] = init((v, self.E))
+        self.emb = torch.nn.Parameter(emb.to(self.device_))
+        self.emb_grad = torch.zeros_like(self.emb)                      # gradient arena (persistently zero)
+        self.emb_touched = torch.zeros((self.total_rows // 32,), dtype=torch.int32, device=self.device_)
+        self.emb._krs_arena = self.emb_grad
+        self.emb._krs_touched = self.emb_touched
 
     # ------------------------------------------------------------------ parameters
     def tables(self):
@@ -174,14 +176,16 @@ class DCN(torch.nn.Module):
             mg=[mk(B, d.units) for d in self.mlp], mdz=[mk(B, d.units) for d in self.mlp],
         )
         self._bufs[B] = b
-        feats = self._feature_list(b["ids"])
-        plan = ops.GatherPlan(feats)
-        tabs = self.tables()
+        b["plan"] = self._make_plan(b["ids"])
+        return b
+
+    def _make_plan(self, ids: torch.Tensor):
+        """Fused-gather descriptor table for a static ids buffer, with the gradient arena wired in."""
+        plan = ops.GatherPlan(self._feature_list(ids))
         for f in range(self.F):
             plan.arr[f].grad = self.emb_grad[self.row_off[f]:].data_ptr()
             plan.arr[f].touched = self.emb_touched[self.row_off[f] // 32:].data_ptr()
-        b["plan"] = plan
-        return b
+        return plan
 
     def forward_backward(self, ids: torch.Tensor, labels: torch.Tensor, denom: int = 0):
         """Forward + backward of one batch through the C ABI only.  ids (B,F) int32 and labels (B,) may
@@ -243,11 +247,15 @@ class DCN(torch.nn.Module):
 
     def train_on_batch(self, ids, labels, optimizer: optimizers.Optimizer, denom: int = 0):
         loss = self.forward_backward(ids, labels, denom)
+        self._sync_gradients()
         optimizer.iterations += 1
         with torch.no_grad():
             optimizer._update(self.emb, self.emb_grad, self.emb_touched)
             optimizer._update(self.dense_flat, self.dense_grad_flat, None)
         return loss
+
+    def _sync_gradients(self):
+        """Single GPU: nothing to exchange."""
 
     def predict(self, ids: torch.Tensor) -> torch.Tensor:
         with torch.no_grad():

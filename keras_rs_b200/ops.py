@@ -94,6 +94,7 @@ class GatherPlan:
             d.reduce = 1 if ids.dim() == 2 else 0
             d.shard_tables = None
             d.shard_grads = None
+            d.shard_touched = None
             d.num_shards = 1
             off += table.shape[1]
             self.keep.append((table, ids, w))
