@@ -50,44 +50,83 @@ __device__ __forceinline__ const float* row_ptr(const krs_feature_t& f, int64_t 
 
 // ------------------------------------------------------------------ forward, fast path
 // Requirements (checked on the host): every feature 1-hot, no weights, same dim E = 4*LPR,
-// out_offset = f*E, out_ld = F*E, single shard.  Rows are numbered r = b*F + f.
-template <int LPR, int UNROLL, typename IdT, bool SHARDED>
-__global__ void __launch_bounds__(256) gather_fast_kernel(const __grid_constant__ GatherParams p) {
-  constexpr int RPW = 32 / LPR;              // rows per warp per step
+// out_offset = f*E, out_ld = F*E.  Rows are numbered r = b*F + f, so the output is one contiguous
+// stream of R = B*F rows.
+//
+// ncu on the first version (profiles/r1_gather_fast_v1.md) showed it bound by the XU pipe (87%: a
+// 64-bit division per row per lane) and the indexed constant cache (78%: p.f[f] per row), with DRAM
+// at 41%.  This version does ONE (b,f) division per 32-row chunk, keeps the per-feature descriptors
+// in shared memory, has each lane resolve ONE row address (ids read coalesced) and hands the row
+// pointers to the LPR-lane groups with shuffles.
+struct FeatLite {
+  const float* table;
+  const void* ids;
+  long long vocab;
+  long long stride;
+  const float* const* shards;
+  int nshards;
+  int shard_shift;   // log2(nshards) when it is a power of two, else -1
+};
+
+template <int LPR, typename IdT, bool SHARDED>
+__global__ void __launch_bounds__(256) gather_fast_kernel(const __grid_constant__ GatherParams p, int chunks_per_warp) {
+  constexpr int RPW = 32 / LPR;              // rows per warp-wide load instruction
+  constexpr int STEPS = LPR;                 // sub-steps to cover a 32-row chunk
+  constexpr int U = STEPS < 8 ? STEPS : 8;   // loads in flight per lane
   constexpr int E = LPR * 4;
-  const int lane = threadIdx.x & 31;
+  __shared__ FeatLite sf[MAXF];
+  for (int i = threadIdx.x; i < p.F; i += blockDim.x) {
+    FeatLite t;
+    t.table = p.f[i].table;
+    t.ids = p.f[i].ids;
+    t.vocab = p.f[i].vocab;
+    t.stride = p.f[i].ids_stride;
+    t.shards = p.f[i].shard_tables;
+    t.nshards = p.f[i].num_shards;
+    t.shard_shift = (t.nshards > 0 && (t.nshards & (t.nshards - 1)) == 0) ? (31 - __clz(t.nshards)) : -1;
+    sf[i] = t;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane % LPR, rsub = lane / LPR;
-  const int64_t R = p.B * p.F;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint32_t F = (uint32_t)p.F;
-  for (int64_t base = wid * (RPW * UNROLL); base < R; base += nwarps * (RPW * UNROLL)) {
-    const float* src[UNROLL];
-#pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      const int64_t r = base + u * RPW + rsub;
-      src[u] = nullptr;
-      if (r < R) {
-        const int64_t b = r / F;
-        const int f = (int)(r - b * F);
-        const krs_feature_t& ft = p.f[f];
-        const int64_t id = clamp_id(load_id<IdT>(ft.ids, b * ft.ids_stride), ft.vocab);
-        if (SHARDED) {
-          const int S = ft.num_shards;
-          src[u] = ft.shard_tables[(int)(id % S)] + (id / S) * E + sub * 4;   // peer-mapped shard: rows cross NVLink here
-        } else {
-          src[u] = ft.table + id * E + sub * 4;
-        }
+  const unsigned F = (unsigned)p.F;
+  const long long R = p.B * (long long)p.F;
+  const long long chunk0 = ((long long)blockIdx.x * 8 + warp) * chunks_per_warp;
+  for (int c = 0; c < chunks_per_warp; ++c) {
+    const long long r0 = (chunk0 + c) * 32;
+    if (r0 >= R) break;
+    // (b,f) of this lane's row: one warp-uniform division, then a carry loop (F may be < 32)
+    long long b = (R < 0x7fffffffLL) ? (long long)((unsigned)r0 / F) : r0 / F;
+    unsigned f = (unsigned)(r0 - b * F) + lane;
+    while (f >= F) { f -= F; ++b; }
+    const float* src = nullptr;
+    if (r0 + lane < R) {
+      const FeatLite& ft = sf[f];
+      const long long id = clamp_id(load_id<IdT>(ft.ids, b * ft.stride), ft.vocab);
+      if (SHARDED) {
+        const int sh = ft.shard_shift;
+        const int owner = sh >= 0 ? (int)(id & (ft.nshards - 1)) : (int)(id % ft.nshards);
+        const long long local = sh >= 0 ? (id >> sh) : (id / ft.nshards);
+        src = ft.shards[owner] + local * E;          // peer-mapped shard: the row crosses NVLink here
+      } else {
+        src = ft.table + id * E;
       }
     }
-    float4 v[UNROLL];
 #pragma unroll
-    for (int u = 0; u < UNROLL; ++u)
-      if (src[u]) v[u] = ldg_nc_f4(src[u]);
+    for (int s0 = 0; s0 < STEPS; s0 += U) {
+      float4 v[U];
+      const float* q[U];
 #pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      const int64_t r = base + u * RPW + rsub;
-      if (src[u]) stg_cs_f4(p.out + r * E + sub * 4, v[u]);
+      for (int u = 0; u < U; ++u) {
+        const int j = (s0 + u) * RPW + rsub;
+        q[u] = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, (unsigned long long)src, j));
+        if (q[u]) v[u] = ldg_nc_f4(q[u] + sub * 4);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int j = (s0 + u) * RPW + rsub;
+        if (q[u]) stg_cs_f4(p.out + (r0 + j) * E + sub * 4, v[u]);
+      }
     }
   }
 }
@@ -373,14 +412,14 @@ bool uniform_onehot(const GatherParams& p, int* E_out, bool* i64, bool* sharded)
 
 template <int LPR, typename IdT, bool SHARDED>
 int launch_fast(const GatherParams& p, cudaStream_t s) {
-  constexpr int UNROLL = (LPR >= 16) ? 4 : 8;
   const int64_t R = p.B * p.F;
-  const int64_t rows_per_warp_step = (32 / LPR) * UNROLL;
-  const int64_t warps_needed = ceil_div<int64_t>(R, rows_per_warp_step);
-  const int64_t blocks_needed = ceil_div<int64_t>(warps_needed, 8);
-  const int64_t cap = (int64_t)sm_count() * 8 * 4;        // up to 4 grid-stride trips beyond full residency
-  const unsigned grid = (unsigned)krs::imax<int64_t>(1, min(blocks_needed, cap));
-  gather_fast_kernel<LPR, UNROLL, IdT, SHARDED><<<grid, 256, 0, s>>>(p);
+  const int64_t chunks = ceil_div<int64_t>(R, 32);
+  // two 32-row chunks per warp keeps ~7 waves of CTAs at C2 (small tail) while amortising the
+  // per-CTA descriptor staging
+  const int chunks_per_warp = chunks >= (int64_t)sm_count() * 8 * 6 * 4 ? 2 : 1;
+  const int64_t blocks_needed = ceil_div<int64_t>(chunks, 8 * chunks_per_warp);
+  const unsigned grid = (unsigned)krs::imax<int64_t>(1, krs::imin<int64_t>(blocks_needed, 0x7fffffff));
+  gather_fast_kernel<LPR, IdT, SHARDED><<<grid, 256, 0, s>>>(p, chunks_per_warp);
   KRS_LAUNCH_CHECK();
   return KRS_OK;
 }

@@ -55,7 +55,7 @@ struct TcArgs {
   int64_t kblocks_per_split;
   int a_mn_major, b_mn_major;
   int atomic_out, accumulate;
-  int mn_lbo, mn_sbo, mn_kstep;   // MN-major descriptor strides (bytes)
+  int mn_lbo, mn_sbo, mn_kstep, mn_layout;   // MN-major descriptor strides (bytes) and UMMA layout type
   Epilogue epi;
 };
 
@@ -134,10 +134,12 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
 __device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile_addr, int kstep) {
   return make_desc(tile_addr + kstep * 32, 16, 512, 4);
 }
-// MN-major tile: blocks of 32 mn x 16 k (2048 B, SWIZZLE_128B); 8-k groups 1024 B apart (SBO),
-// mn blocks 2048 B apart (LBO); k-step = +1024 B.
+// MN-major tile (32-bit elements): blocks of 32 mn x 16 k (2048 B).  For tf32 the ONLY MN-major layout
+// the tensor core accepts is SWIZZLE_128B_BASE32B (layout type 1; cutlass sm100_common.inl:92): 32-byte
+// chunks swizzled within a 128-byte row over groups of 4 k-rows — TMA mode SWIZZLE_128B_ATOM_32B.
+// 4-k groups are 512 B apart (SBO), mn blocks 2048 B apart (LBO); a k-step (8 rows) = +1024 B.
 __device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile_addr, int kstep, const TcArgs& g) {
-  return make_desc(tile_addr + kstep * g.mn_kstep, g.mn_lbo, g.mn_sbo, 2);
+  return make_desc(tile_addr + kstep * g.mn_kstep, g.mn_lbo, g.mn_sbo, (uint32_t)g.mn_layout);
 }
 
 __device__ __forceinline__ float tf32_rna_f(float x) {
@@ -469,7 +471,10 @@ int gemm_tc(const float* A, int64_t lda, bool transA, const float* B, int64_t ld
   g.atomic_out = g.splits > 1 ? 1 : 0;
   g.accumulate = accumulate ? 1 : 0;
   g.epi = epi;
-  g.mn_lbo = 2048; g.mn_sbo = 1024; g.mn_kstep = 1024;
+  g.mn_lbo = 2048; g.mn_sbo = 512; g.mn_kstep = 1024; g.mn_layout = 1;
+  int mn_swz = (int)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+  if (const char* e = getenv("KRS_TC_MN_LAYOUT")) g.mn_layout = atoi(e);
+  if (const char* e = getenv("KRS_TC_MN_SWZ")) mn_swz = atoi(e);
   if (const char* e = getenv("KRS_TC_MN_LBO")) g.mn_lbo = atoi(e);       // debug overrides
   if (const char* e = getenv("KRS_TC_MN_SBO")) g.mn_sbo = atoi(e);
   if (const char* e = getenv("KRS_TC_MN_KSTEP")) g.mn_kstep = atoi(e);
@@ -477,10 +482,10 @@ int gemm_tc(const float* A, int64_t lda, bool transA, const float* B, int64_t ld
   CUtensorMap ma, mb;
   bool ok;
   if (!g.a_mn_major) ok = make_map(&ma, A, M, K, lda, BK, BM, CU_TENSOR_MAP_SWIZZLE_64B);        // [M][K]
-  else ok = make_map(&ma, A, K, M, lda, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B);                     // [K][M]
+  else ok = make_map(&ma, A, K, M, lda, 32, BK, (CUtensorMapSwizzle)mn_swz);                     // [K][M]
   if (!ok) return KRS_EUNSUPPORTED;
   if (!g.b_mn_major) ok = make_map(&mb, B, N, K, ldb, BK, g.bn, CU_TENSOR_MAP_SWIZZLE_64B);      // [N][K]
-  else ok = make_map(&mb, B, K, N, ldb, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B);                     // [K][N]
+  else ok = make_map(&mb, B, K, N, ldb, 32, BK, (CUtensorMapSwizzle)mn_swz);                     // [K][N]
   if (!ok) return KRS_EUNSUPPORTED;
 
   if (g.atomic_out && !accumulate)
