@@ -16,7 +16,14 @@
 //   warps 2-5   converters: shared -> registers -> shared, write hi (in place) and lo tiles
 //   warps 6-9   epilogue: tcgen05.ld accumulator rows -> registers -> fused epilogue -> global
 // Shared memory ring: 4 stages x (A_raw | B_raw | A_lo | B_lo), BK = 16 floats per stage.
-// TMEM: 512 columns = 2 accumulator stages x 256 columns (128 lanes = the 128 rows of the tile).
+// TMEM: 512 columns = TWO accumulators x 256 columns (128 lanes = the 128 rows of the tile): the hi·hi
+// products and the small cross terms (lo·hi + hi·lo) accumulate separately and are added in fp32
+// registers by the epilogue.  Reason (measured, tests/test_gpu_tc.py): the tensor core's fp32
+// accumulate truncates, so the error grows with the number of accumulations into one TMEM tile
+// (~0.5 * 6e-8 per step, systematic).  Keeping the small terms out of the main accumulator cuts the
+// step count 3x; long reductions (the batch-dimension weight gradients) are additionally split so
+// that no accumulator sees more than KC_MAX/8 steps, partial tiles being combined with fp32 RED
+// (round-to-nearest) in global memory.
 //
 // Operand layouts: K-contiguous operands use 64-byte rows with SWIZZLE_64B (K-major UMMA
 // descriptors), MN-contiguous operands (x^T, dz in the weight-gradient GEMM, V in the forward) use
@@ -41,6 +48,7 @@ constexpr int STAGES = 4;
 constexpr int MAX_BN = 256;
 constexpr int NUM_THREADS = 320;
 constexpr int A_BYTES = BM * BK * 4;             // 8192
+constexpr int KC_MAX = 1024;                     // max K elements accumulated inside one TMEM tile
 constexpr int SPIN_LIMIT = 1 << 26;              // turns a protocol bug into a trap instead of a hang
 
 std::atomic<long long> g_tc_launches{0};
@@ -55,6 +63,7 @@ struct TcArgs {
   int64_t kblocks_per_split;
   int a_mn_major, b_mn_major;
   int atomic_out, accumulate;
+  int no_mask;            // 1: leave hi = raw fp32 bits (hardware ignores the low 13 mantissa bits)
   int mn_lbo, mn_sbo, mn_kstep, mn_layout;   // MN-major descriptor strides (bytes) and UMMA layout type
   Epilogue epi;
 };
@@ -237,10 +246,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_init(&conv_bar[s], 4);      // one arrival per converter warp
       mbar_init(&empty_bar[s], 1);
     }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 4);    // one arrival per epilogue warp
-    }
+    mbar_init(&tmem_full[0], 1);
+    mbar_init(&tmem_empty[0], 4);      // one arrival per epilogue warp
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -295,15 +302,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                            ((uint32_t)g.b_mn_major << 16) | ((uint32_t)(g.bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
     int stage = 0;
     uint32_t phase = 0;
-    int acc = 0;
     uint32_t acc_phase = 0;
+    const uint32_t d_main = tmem_base;
+    const uint32_t d_small = tmem_base + (uint32_t)MAX_BN;
     for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int split = (int)(tile / tiles_mn);
       const int64_t kb0 = (int64_t)split * g.kblocks_per_split;
       const int64_t kb1 = imin<int64_t>(g.kblocks_total, kb0 + g.kblocks_per_split);
-      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      mbar_wait(&tmem_empty[0], acc_phase ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * MAX_BN);
       for (int64_t kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&conv_bar[stage], phase);
         tc_fence_after();
@@ -319,18 +326,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const uint64_t dbh = g.b_mn_major ? desc_mnmajor(b_hi, ks, g) : desc_kmajor(b_hi, ks);
             const uint64_t dbl = g.b_mn_major ? desc_mnmajor(b_lo, ks, g) : desc_kmajor(b_lo, ks);
             const uint32_t first = (kb == kb0 && ks == 0) ? 0u : 1u;
-            tc_mma_tf32(d_tmem, dal, dbh, idesc, first);     // small terms first
-            tc_mma_tf32(d_tmem, dah, dbl, idesc, 1u);
-            tc_mma_tf32(d_tmem, dah, dbh, idesc, 1u);
+            tc_mma_tf32(d_small, dal, dbh, idesc, first);    // cross terms: their own accumulator
+            tc_mma_tf32(d_small, dah, dbl, idesc, 1u);
+            tc_mma_tf32(d_main, dah, dbh, idesc, first);     // main term
           }
           tc_commit(&empty_bar[stage]);                       // frees the stage when these MMAs retire
-          if (kb == kb1 - 1) tc_commit(&tmem_full[acc]);      // accumulator complete
+          if (kb == kb1 - 1) tc_commit(&tmem_full[0]);        // accumulators complete
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      if (kb1 <= kb0 && lane == 0) tc_commit(&tmem_full[acc]);   // empty K range (K == 0): nothing accumulated
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (kb1 <= kb0 && lane == 0) tc_commit(&tmem_full[0]);  // empty K range: nothing accumulated
+      acc_phase ^= 1;
     }
   } else if (warp < 6) {
     // ======================= converters (128 threads) =======================
@@ -357,7 +364,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           l.y = tf32_rna_f(x.y - h.y);
           l.z = tf32_rna_f(x.z - h.z);
           l.w = tf32_rna_f(x.w - h.w);
-          raw[i] = h;
+          if (!g.no_mask) raw[i] = h;
           lo[i] = l;
         }
         // generic-proxy writes must be visible to the tensor core (async proxy) before the MMA reads them
@@ -370,33 +377,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   } else {
     // ======================= epilogue (warps 6..9) =======================
     const int quad = warp & 3;              // TMEM lane quadrant this warp may read
-    int acc = 0;
     uint32_t acc_phase = 0;
     for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int split = (int)(tile / tiles_mn);
       const int64_t rem = tile - (int64_t)split * tiles_mn;
       const int tn = (int)(rem / g.tiles_m);
       const int tm = (int)(rem - (int64_t)tn * g.tiles_m);
-      mbar_wait(&tmem_full[acc], acc_phase);
+      mbar_wait(&tmem_full[0], acc_phase);
       tc_fence_after();
       const int64_t m = (int64_t)tm * BM + quad * 32 + lane;
-      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * MAX_BN);
+      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16);
       const bool empty_k = ((int64_t)split * g.kblocks_per_split) >= g.kblocks_total;
       for (int c = 0; c < g.bn; c += 16) {
-        uint32_t r[16];
+        uint32_t r[16], r2[16];
         tc_ld16(t_row + (uint32_t)c, r);
+        tc_ld16(t_row + (uint32_t)(MAX_BN + c), r2);
         tc_wait_ld();
-        if (empty_k) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) r[j] = 0u;
-        }
+        for (int j = 0; j < 16; ++j)
+          r[j] = empty_k ? 0u : __float_as_uint(__fadd_rn(__uint_as_float(r[j]), __uint_as_float(r2[j])));
         const int64_t n0 = (int64_t)tn * g.bn + c;
         if (m < g.M && n0 < g.N) epilogue_row16(g, m, n0, r);
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (lane == 0) mbar_arrive(&tmem_empty[0]);
+      acc_phase ^= 1;
     }
   }
 
@@ -457,6 +463,9 @@ int gemm_tc(const float* A, int64_t lda, bool transA, const float* B, int64_t ld
   if (split_k < 1) split_k = 1;
   KRS_REQUIRE(split_k == 1 || epi.kind == EPI_NONE, "gemm_tc: split-K only with the plain epilogue");
   if (encode_fn() == nullptr) return KRS_EUNSUPPORTED;
+  // bound the number of truncating accumulations per TMEM tile (see the header): plain-epilogue GEMMs
+  // with a long reduction are split so that each partial tile covers at most KC_MAX of K
+  if (epi.kind == EPI_NONE && !accumulate && K > KC_MAX) split_k = (int)imax<int64_t>(split_k, ceil_div<int64_t>(K, KC_MAX));
 
   TcArgs g;
   g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K;
@@ -471,6 +480,8 @@ int gemm_tc(const float* A, int64_t lda, bool transA, const float* B, int64_t ld
   g.atomic_out = g.splits > 1 ? 1 : 0;
   g.accumulate = accumulate ? 1 : 0;
   g.epi = epi;
+  g.no_mask = 0;
+  if (const char* e = getenv("KRS_TC_NO_MASK")) g.no_mask = atoi(e);
   g.mn_lbo = 2048; g.mn_sbo = 512; g.mn_kstep = 1024; g.mn_layout = 1;
   int mn_swz = (int)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
   if (const char* e = getenv("KRS_TC_MN_LAYOUT")) g.mn_layout = atoi(e);

@@ -97,3 +97,24 @@ def test_tc_dcn_step_matches_ffma_engine(tc):
     np.testing.assert_allclose(loss_tc, loss_ff, rtol=1e-5)
     assert_close(npy(g_tc), npy(m.dense_grad_flat), what="dense grads tc vs ffma")
     assert_close(npy(e_tc), npy(m.emb_grad), what="emb grads tc vs ffma")
+
+
+def test_tc_full_size_accuracy_c2_shapes(tc):
+    """BASELINE C2 shapes (B=65536, D=832): forward x@V and the batch-reduction weight gradient x^T dz
+    against float64 products computed independently on the device."""
+    g = torch.Generator(device="cuda").manual_seed(7)
+    B, D = 65536, 832
+    x = torch.randn((B, D), device="cuda", generator=g)
+    V = (torch.rand((D, D), device="cuda", generator=g) * 2 - 1) * 0.06
+    dz = torch.randn((B, D), device="cuda", generator=g)
+    before = _count(tc)
+    y = tc.ops.sgemm(x, V)                       # NN, K = 832
+    dV = tc.ops.sgemm(x, dz, True, False)        # TN, K = 65536 (split + RED)
+    dx = tc.ops.sgemm(dz, V, False, True)        # NT
+    assert _count(tc) == before + 3
+    for got, ref, what in ((y, x.double() @ V.double(), "fwd"), (dV, x.double().T @ dz.double(), "dV"),
+                           (dx, dz.double() @ V.double().T, "dx")):
+        err = float((got.double() - ref).abs().max())
+        scale = float(ref.abs().max())
+        assert err <= 1e-5 * scale, f"{what}: max abs err {err:.3e} > 1e-5 * {scale:.3e}"
+        print(f"tc accuracy {what}: max abs err / max|ref| = {err / scale:.2e}")
