@@ -63,6 +63,7 @@ struct TcArgs {
   int64_t kblocks_per_split;
   int a_mn_major, b_mn_major;
   int atomic_out, accumulate;
+  int epi_vec;            // rows of C / h2 / z / aux streams are 16-byte aligned (vector epilogue)
   int no_mask;            // 1: leave hi = raw fp32 bits (hardware ignores the low 13 mantissa bits)
   int mn_lbo, mn_sbo, mn_kstep, mn_layout;   // MN-major descriptor strides (bytes) and UMMA layout type
   Epilogue epi;
@@ -158,64 +159,94 @@ __device__ __forceinline__ float tf32_rna_f(float x) {
 }
 
 // ---------------------------------------------------------------- fused epilogue on 16 columns of one row
-__device__ __forceinline__ void epilogue_row16(const TcArgs& g, int64_t m, int64_t n0, const uint32_t (&acc)[16]) {
+// The two per-element operand streams of the epilogue (CROSS: x0, x ; ADD2: add1, add2) are prefetched
+// one 16-column chunk ahead by the caller (Aux16), so their global-memory latency overlaps the TMEM
+// loads and the arithmetic of the previous chunk instead of sitting on the critical path.
+struct Aux16 {
+  float4 v[4];
+};
+__device__ __forceinline__ const float* epi_stream1(const Epilogue& e) {
+  return e.kind == EPI_CROSS ? e.x0 : (e.kind == EPI_ADD2 ? e.add1 : nullptr);
+}
+__device__ __forceinline__ const float* epi_stream2(const Epilogue& e) {
+  return e.kind == EPI_CROSS ? e.x : (e.kind == EPI_ADD2 ? e.add2 : nullptr);
+}
+__device__ __forceinline__ void aux_prefetch(const float* p, int64_t off, bool ok, Aux16& a) {
+  if (p != nullptr && ok) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) a.v[q] = *reinterpret_cast<const float4*>(p + off + 4 * q);
+  }
+}
+
+// full: the chunk is 16 in-range columns with 16-byte aligned rows (aux streams were prefetched)
+__device__ __forceinline__ void epilogue_row16(const TcArgs& g, int64_t m, int64_t n0, const uint32_t (&acc)[16], bool full,
+                                               const Aux16& a1, const Aux16& a2) {
   const Epilogue& e = g.epi;
   const int64_t off = m * g.ldc + n0;
   const int cnt = (int)imin<int64_t>(16, g.N - n0);
   if (cnt <= 0) return;
   if (g.atomic_out) {
-    for (int j = 0; j < cnt; ++j) atomicAdd(g.C + off + j, __uint_as_float(acc[j]));
+    if (full) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)   // 16-byte vector reductions (RED.E.ADD.F32x4), round-to-nearest in L2
+        atomicAdd(reinterpret_cast<float4*>(g.C + off + 4 * q),
+                  make_float4(__uint_as_float(acc[4 * q]), __uint_as_float(acc[4 * q + 1]), __uint_as_float(acc[4 * q + 2]),
+                              __uint_as_float(acc[4 * q + 3])));
+    } else {
+      for (int j = 0; j < cnt; ++j) atomicAdd(g.C + off + j, __uint_as_float(acc[j]));
+    }
     return;
   }
-  const bool vec = (cnt == 16) && ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15u) == 0) && ((n0 & 3) == 0);
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    float v[4], out[4], h2v[4], zv[4];
+    float v[4], out[4], h2v[4], zv[4], s1[4], s2[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) v[j] = __uint_as_float(acc[q * 4 + j]);
     const int64_t o = off + q * 4;
     const int64_t n = n0 + q * 4;
-    const int c4 = vec ? 4 : (int)imax<int64_t>(0, imin<int64_t>(4, g.N - n));
+    const int c4 = full ? 4 : (int)imax<int64_t>(0, imin<int64_t>(4, g.N - n));
     if (c4 <= 0) break;
+    const float* p1 = epi_stream1(e);
+    const float* p2 = epi_stream2(e);
+    if (full) {
+      s1[0] = a1.v[q].x; s1[1] = a1.v[q].y; s1[2] = a1.v[q].z; s1[3] = a1.v[q].w;
+      s2[0] = a2.v[q].x; s2[1] = a2.v[q].y; s2[2] = a2.v[q].z; s2[3] = a2.v[q].w;
+    } else {
+      for (int j = 0; j < c4; ++j) {
+        s1[j] = p1 ? p1[o + j] : 0.f;
+        s2[j] = p2 ? p2[o + j] : 0.f;
+      }
+    }
     if (e.kind == EPI_NONE) {
       for (int j = 0; j < c4; ++j) out[j] = v[j] + (g.accumulate ? g.C[o + j] : 0.f);
     } else if (e.kind == EPI_BIAS_ACT) {
       for (int j = 0; j < c4; ++j) out[j] = act_apply(e.act, v[j] + (e.bias ? e.bias[n + j] : 0.f));
     } else if (e.kind == EPI_CROSS) {
-      float x0v[4], xv[4];
-      if (vec) {
-        const float4 a = *reinterpret_cast<const float4*>(e.x0 + o);
-        const float4 b = *reinterpret_cast<const float4*>(e.x + o);
-        x0v[0] = a.x; x0v[1] = a.y; x0v[2] = a.z; x0v[3] = a.w;
-        xv[0] = b.x; xv[1] = b.y; xv[2] = b.z; xv[3] = b.w;
-      } else {
-        for (int j = 0; j < c4; ++j) { x0v[j] = e.x0[o + j]; xv[j] = e.x[o + j]; }
-      }
       for (int j = 0; j < c4; ++j) {
         const float z = v[j] + (e.bias ? e.bias[n + j] : 0.f);
         const float a = act_apply(e.act, z);
-        const float h2 = (e.diag != 0.f) ? a + e.diag * xv[j] : a;
+        const float h2 = (e.diag != 0.f) ? a + e.diag * s2[j] : a;
         zv[j] = z;
         h2v[j] = h2;
-        out[j] = x0v[j] * h2 + xv[j];
+        out[j] = s1[j] * h2 + s2[j];                   // x0 * h2 + x  (feature_cross.py:194)
       }
       if (e.h2_out) {
-        if (vec) *reinterpret_cast<float4*>(e.h2_out + o) = make_float4(h2v[0], h2v[1], h2v[2], h2v[3]);
+        if (full) *reinterpret_cast<float4*>(e.h2_out + o) = make_float4(h2v[0], h2v[1], h2v[2], h2v[3]);
         else for (int j = 0; j < c4; ++j) e.h2_out[o + j] = h2v[j];
       }
       if (e.z_out) {
-        if (vec) *reinterpret_cast<float4*>(e.z_out + o) = make_float4(zv[0], zv[1], zv[2], zv[3]);
+        if (full) *reinterpret_cast<float4*>(e.z_out + o) = make_float4(zv[0], zv[1], zv[2], zv[3]);
         else for (int j = 0; j < c4; ++j) e.z_out[o + j] = zv[j];
       }
     } else {  // EPI_ADD2
       for (int j = 0; j < c4; ++j) {
         float r = v[j];
-        if (e.add1) r += e.alpha1 * e.add1[o + j];
-        if (e.add2) r += e.alpha2 * e.add2[o + j];
+        if (p1) r += e.alpha1 * s1[j];
+        if (p2) r += e.alpha2 * s2[j];
         out[j] = r;
       }
     }
-    if (vec) *reinterpret_cast<float4*>(g.C + o) = make_float4(out[0], out[1], out[2], out[3]);
+    if (full) *reinterpret_cast<float4*>(g.C + o) = make_float4(out[0], out[1], out[2], out[3]);
     else for (int j = 0; j < c4; ++j) g.C[o + j] = out[j];
   }
 }
@@ -225,7 +256,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const TcArgs g) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // carve: stages first (1024-aligned), then barriers
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // align by OFFSET (not by integer round trip) so the compiler keeps the shared address space (LDS/STS,
+  // not generic LD/ST — ncu on the first version showed generic accesses in the converter)
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int b_bytes = g.bn * BK * 4;
   const int raw_bytes = A_BYTES + b_bytes;
   const int stage_bytes = 2 * raw_bytes;
@@ -270,8 +303,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int split = (int)(tile / tiles_mn);
         const int64_t rem = tile - (int64_t)split * tiles_mn;
-        const int tn = (int)(rem / g.tiles_m);
-        const int tm = (int)(rem - (int64_t)tn * g.tiles_m);
+        const int tm = (int)(rem / g.tiles_n);
+        const int tn = (int)(rem - (int64_t)tm * g.tiles_n);
         const int64_t kb0 = (int64_t)split * g.kblocks_per_split;
         const int64_t kb1 = imin<int64_t>(g.kblocks_total, kb0 + g.kblocks_per_split);
         for (int64_t kb = kb0; kb < kb1; ++kb) {
@@ -353,19 +386,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         mbar_wait(&full_bar[stage], phase);
         float4* raw = reinterpret_cast<float4*>(smem + (size_t)stage * stage_bytes);
         float4* lo = reinterpret_cast<float4*>(smem + (size_t)stage * stage_bytes + raw_bytes);
-        for (int i = ct; i < nvec; i += 128) {
-          const float4 x = raw[i];
-          float4 h, l;
-          h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
-          h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
-          h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
-          h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
-          l.x = tf32_rna_f(x.x - h.x);
-          l.y = tf32_rna_f(x.y - h.y);
-          l.z = tf32_rna_f(x.z - h.z);
-          l.w = tf32_rna_f(x.w - h.w);
-          if (!g.no_mask) raw[i] = h;
-          lo[i] = l;
+        // all loads first (<= 12 float4 per thread at bn = 256), then split + store: one shared-memory
+        // latency per k-block instead of one per element
+        constexpr int MAXV = (A_BYTES + MAX_BN * BK * 4) / 16 / 128;   // 12
+        float4 xv[MAXV];
+#pragma unroll
+        for (int j = 0; j < MAXV; ++j) {
+          const int i = ct + j * 128;
+          if (i < nvec) xv[j] = raw[i];
+        }
+#pragma unroll
+        for (int j = 0; j < MAXV; ++j) {
+          const int i = ct + j * 128;
+          if (i < nvec) {
+            const float4 x = xv[j];
+            float4 h, l;
+            h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+            h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+            h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+            h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+            l.x = tf32_rna_f(x.x - h.x);
+            l.y = tf32_rna_f(x.y - h.y);
+            l.z = tf32_rna_f(x.z - h.z);
+            l.w = tf32_rna_f(x.w - h.w);
+            if (!g.no_mask) raw[i] = h;
+            lo[i] = l;
+          }
         }
         // generic-proxy writes must be visible to the tensor core (async proxy) before the MMA reads them
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -381,14 +427,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int split = (int)(tile / tiles_mn);
       const int64_t rem = tile - (int64_t)split * tiles_mn;
-      const int tn = (int)(rem / g.tiles_m);
-      const int tm = (int)(rem - (int64_t)tn * g.tiles_m);
+      const int tm = (int)(rem / g.tiles_n);
+      const int tn = (int)(rem - (int64_t)tm * g.tiles_n);
+      const int64_t m = (int64_t)tm * BM + quad * 32 + lane;
+      const float* p1 = epi_stream1(g.epi);
+      const float* p2 = epi_stream2(g.epi);
+      const int64_t nbase = (int64_t)tn * g.bn;
+      auto chunk_full = [&](int c) { return g.epi_vec && m < g.M && (nbase + c + 16) <= g.N; };
+      Aux16 a1, a2, b1, b2;
+      // first chunk's operands are requested BEFORE waiting for the accumulator
+      aux_prefetch(p1, m * g.ldc + nbase, chunk_full(0), a1);
+      aux_prefetch(p2, m * g.ldc + nbase, chunk_full(0), a2);
       mbar_wait(&tmem_full[0], acc_phase);
       tc_fence_after();
-      const int64_t m = (int64_t)tm * BM + quad * 32 + lane;
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16);
       const bool empty_k = ((int64_t)split * g.kblocks_per_split) >= g.kblocks_total;
       for (int c = 0; c < g.bn; c += 16) {
+        if (c + 16 < g.bn) {
+          aux_prefetch(p1, m * g.ldc + nbase + c + 16, chunk_full(c + 16), b1);
+          aux_prefetch(p2, m * g.ldc + nbase + c + 16, chunk_full(c + 16), b2);
+        }
         uint32_t r[16], r2[16];
         tc_ld16(t_row + (uint32_t)c, r);
         tc_ld16(t_row + (uint32_t)(MAX_BN + c), r2);
@@ -396,8 +454,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
         for (int j = 0; j < 16; ++j)
           r[j] = empty_k ? 0u : __float_as_uint(__fadd_rn(__uint_as_float(r[j]), __uint_as_float(r2[j])));
-        const int64_t n0 = (int64_t)tn * g.bn + c;
-        if (m < g.M && n0 < g.N) epilogue_row16(g, m, n0, r);
+        const int64_t n0 = nbase + c;
+        if (m < g.M && n0 < g.N) epilogue_row16(g, m, n0, r, chunk_full(c), a1, a2);
+        a1 = b1;
+        a2 = b2;
       }
       tc_fence_before();
       __syncwarp();
@@ -480,6 +540,11 @@ int gemm_tc(const float* A, int64_t lda, bool transA, const float* B, int64_t ld
   g.atomic_out = g.splits > 1 ? 1 : 0;
   g.accumulate = accumulate ? 1 : 0;
   g.epi = epi;
+  {
+    auto ok16 = [](const void* q) { return q == nullptr || aligned16(q); };
+    g.epi_vec = ((ldc % 4) == 0 && aligned16(C) && ok16(epi.x0) && ok16(epi.x) && ok16(epi.h2_out) && ok16(epi.z_out) &&
+                 ok16(epi.add1) && ok16(epi.add2) && (g.bn % 16) == 0 && ((int64_t)g.bn % 4) == 0) ? 1 : 0;
+  }
   g.no_mask = 0;
   if (const char* e = getenv("KRS_TC_NO_MASK")) g.no_mask = atoi(e);
   g.mn_lbo = 2048; g.mn_sbo = 512; g.mn_kstep = 1024; g.mn_layout = 1;
