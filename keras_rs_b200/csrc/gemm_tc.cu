@@ -13,8 +13,9 @@
 //   warp 0      TMA producer: cp.async.bulk.tensor fp32 tiles global -> shared (mbarrier complete_tx)
 //   warp 1      MMA issuer: one elected lane issues tcgen05.mma.kind::tf32 (SS operands, D in TMEM),
 //               tcgen05.commit releases shared-memory stages / publishes the accumulator
-//   warps 2-5   converters: shared -> registers -> shared, write hi (in place) and lo tiles
-//   warps 6-9   epilogue: tcgen05.ld accumulator rows -> registers -> fused epilogue -> global
+//   warps 2-5   epilogue: tcgen05.ld accumulator rows -> registers -> fused epilogue -> global
+//   warps 6-9   converters: shared -> registers -> shared, write hi (in place) and lo tiles (highest
+//               warp ids: the scheduler arbitrates highest-warp-id first and they are the critical stage)
 // Shared memory ring: 4 stages x (A_raw | B_raw | A_lo | B_lo), BK = 16 floats per stage.
 // TMEM: 512 columns = TWO accumulators x 256 columns (128 lanes = the 128 rows of the tile): the hi·hi
 // products and the small cross terms (lo·hi + hi·lo) accumulate separately and are added in fp32
@@ -96,6 +97,27 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(addr), "r"(parity)
         : "memory");
     if (ok) break;
+    if (++spins > SPIN_LIMIT) __trap();
+  }
+}
+// Long waits (producer on a free stage, epilogue on the accumulator) back off with nanosleep: a spinning
+// warp steals issue slots from the converter warps that share its scheduler (ncu, profiles/r1_gemm_tc.md).
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok = 0;
+  int spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x2000;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) break;
+    __nanosleep(128);
     if (++spins > SPIN_LIMIT) __trap();
   }
 }
@@ -297,36 +319,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   if (warp == 0) {
     // ======================= TMA producer =======================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int split = (int)(tile / tiles_mn);
-        const int64_t rem = tile - (int64_t)split * tiles_mn;
-        const int tm = (int)(rem / g.tiles_n);
-        const int tn = (int)(rem - (int64_t)tm * g.tiles_n);
-        const int64_t kb0 = (int64_t)split * g.kblocks_per_split;
-        const int64_t kb1 = imin<int64_t>(g.kblocks_total, kb0 + g.kblocks_per_split);
-        for (int64_t kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          unsigned char* st = smem + (size_t)stage * stage_bytes;
-          mbar_expect_tx(&full_bar[stage], (uint32_t)raw_bytes);
-          const int k0 = (int)(kb * BK);
-          if (!g.a_mn_major) {
-            tma_load_2d(st, &tmap_a, k0, tm * BM, &full_bar[stage]);                  // box {16 k, 128 m}
-          } else {
-            for (int blk = 0; blk < BM / 32; ++blk)
-              tma_load_2d(st + blk * 2048, &tmap_a, tm * BM + blk * 32, k0, &full_bar[stage]);   // box {32 m, 16 k}
-          }
+    // every lane waits for the free stage; lane 0 arms the transaction count, then the boxes of the stage
+    // (1 per K-major operand, bn/32 or 4 per MN-major operand) are issued by different lanes in parallel
+    int stage = 0;
+    uint32_t phase = 0;
+    const int nA = g.a_mn_major ? BM / 32 : 1;
+    const int nB = g.b_mn_major ? g.bn / 32 : 1;
+    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int split = (int)(tile / tiles_mn);
+      const int64_t rem = tile - (int64_t)split * tiles_mn;
+      const int tm = (int)(rem / g.tiles_n);
+      const int tn = (int)(rem - (int64_t)tm * g.tiles_n);
+      const int64_t kb0 = (int64_t)split * g.kblocks_per_split;
+      const int64_t kb1 = imin<int64_t>(g.kblocks_total, kb0 + g.kblocks_per_split);
+      for (int64_t kb = kb0; kb < kb1; ++kb) {
+        mbar_wait_relaxed(&empty_bar[stage], phase ^ 1);
+        unsigned char* st = smem + (size_t)stage * stage_bytes;
+        if (lane == 0) mbar_expect_tx(&full_bar[stage], (uint32_t)raw_bytes);
+        __syncwarp();
+        const int k0 = (int)(kb * BK);
+        if (lane < nA) {
+          if (!g.a_mn_major) tma_load_2d(st, &tmap_a, k0, tm * BM, &full_bar[stage]);                       // box {16 k, 128 m}
+          else tma_load_2d(st + lane * 2048, &tmap_a, tm * BM + lane * 32, k0, &full_bar[stage]);          // box {32 m, 16 k}
+        } else if (lane < nA + nB) {
+          const int blk = lane - nA;
           unsigned char* sb = st + A_BYTES;
-          if (!g.b_mn_major) {
-            tma_load_2d(sb, &tmap_b, k0, tn * g.bn, &full_bar[stage]);                // box {16 k, bn n}
-          } else {
-            for (int blk = 0; blk < g.bn / 32; ++blk)
-              tma_load_2d(sb + blk * 2048, &tmap_b, tn * g.bn + blk * 32, k0, &full_bar[stage]);
-          }
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (!g.b_mn_major) tma_load_2d(sb, &tmap_b, k0, tn * g.bn, &full_bar[stage]);                     // box {16 k, bn n}
+          else tma_load_2d(sb + blk * 2048, &tmap_b, tn * g.bn + blk * 32, k0, &full_bar[stage]);
         }
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -342,7 +363,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int split = (int)(tile / tiles_mn);
       const int64_t kb0 = (int64_t)split * g.kblocks_per_split;
       const int64_t kb1 = imin<int64_t>(g.kblocks_total, kb0 + g.kblocks_per_split);
-      mbar_wait(&tmem_empty[0], acc_phase ^ 1);
+      mbar_wait_relaxed(&tmem_empty[0], acc_phase ^ 1);
       tc_fence_after();
       for (int64_t kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&conv_bar[stage], phase);
@@ -372,9 +393,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       if (kb1 <= kb0 && lane == 0) tc_commit(&tmem_full[0]);  // empty K range: nothing accumulated
       acc_phase ^= 1;
     }
-  } else if (warp < 6) {
-    // ======================= converters (128 threads) =======================
-    const int ct = threadIdx.x - 64;        // 0..127
+  } else if (warp >= 6) {
+    // ======================= converters (warps 6..9: highest warp ids = highest issue priority) ===========
+    const int ct = threadIdx.x - 192;       // 0..127
     int stage = 0;
     uint32_t phase = 0;
     const int nvec = raw_bytes / 16;
@@ -421,7 +442,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     }
   } else {
-    // ======================= epilogue (warps 6..9) =======================
+    // ======================= epilogue (warps 2..5) =======================
     const int quad = warp & 3;              // TMEM lane quadrant this warp may read
     uint32_t acc_phase = 0;
     for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -438,7 +459,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       // first chunk's operands are requested BEFORE waiting for the accumulator
       aux_prefetch(p1, m * g.ldc + nbase, chunk_full(0), a1);
       aux_prefetch(p2, m * g.ldc + nbase, chunk_full(0), a2);
-      mbar_wait(&tmem_full[0], acc_phase);
+      mbar_wait_relaxed(&tmem_full[0], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16);
       const bool empty_k = ((int64_t)split * g.kblocks_per_split) >= g.kblocks_total;
