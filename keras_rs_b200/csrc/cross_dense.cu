@@ -146,6 +146,76 @@ __global__ void axpy_mul_kernel(float* __restrict__ y, const float* __restrict__
     y[i] += alpha * a[i] * b[i];
 }
 
+
+// ------------------------------------------------------------------ skinny Dense (N <= 8, e.g. the final Dense(1))
+// A 128-wide GEMM tile wastes >99% of its work on a 1-column output; these are single streaming passes.
+template <int NMAX>
+__global__ void __launch_bounds__(256) dense_skinny_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W,
+                                                               const float* __restrict__ b, float* __restrict__ y, int64_t M,
+                                                               int K, int N, int act) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t m = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; m < M; m += nwarps) {
+    float acc[NMAX];
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n) acc[n] = 0.f;
+    const float* xr = x + m * K;
+    for (int k = lane; k < K; k += 32) {
+      const float xv = xr[k];
+#pragma unroll
+      for (int n = 0; n < NMAX; ++n)
+        if (n < N) acc[n] = fmaf(xv, W[(int64_t)k * N + n], acc[n]);
+    }
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n)
+      for (int o = 16; o > 0; o >>= 1) acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], o);
+    if (lane == 0) {
+#pragma unroll
+      for (int n = 0; n < NMAX; ++n)
+        if (n < N) y[m * N + n] = act_apply(act, acc[n] + (b ? b[n] : 0.f));
+    }
+  }
+}
+
+// dW[k][n] += sum_m x[m][k] * dz[m][n]   (dW pre-zeroed); block = row chunk, thread = column k
+template <int NMAX>
+__global__ void __launch_bounds__(256) dense_skinny_dw_kernel(const float* __restrict__ x, const float* __restrict__ dz,
+                                                              float* __restrict__ dW, int64_t M, int K, int N,
+                                                              int rows_per_block) {
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = min(M, r0 + rows_per_block);
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    float acc[NMAX];
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n) acc[n] = 0.f;
+    for (int64_t m = r0; m < r1; ++m) {
+      const float xv = x[m * K + k];
+#pragma unroll
+      for (int n = 0; n < NMAX; ++n)
+        if (n < N) acc[n] = fmaf(xv, dz[m * N + n], acc[n]);
+    }
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n)
+      if (n < N) atomicAdd(dW + (int64_t)k * N + n, acc[n]);
+  }
+}
+
+// dx[m][k] = sum_n dz[m][n] * W[k][n]
+template <int NMAX>
+__global__ void __launch_bounds__(256) dense_skinny_dx_kernel(const float* __restrict__ dz, const float* __restrict__ W,
+                                                              float* __restrict__ dx, int64_t M, int K, int N) {
+  const int64_t total = M * (int64_t)K;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / K;
+    const int k = (int)(i - m * K);
+    float acc = 0.f;
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n)
+      if (n < N) acc = fmaf(dz[m * N + n], W[(int64_t)k * N + n], acc);
+    dx[i] = acc;
+  }
+}
+
 // loss: kind 0 MSE, 1 BCE(prob), 2 BCE(logits).  loss pre-zeroed; mean over B.
 __global__ void loss_kernel(const float* __restrict__ pred, const float* __restrict__ label, float* __restrict__ loss,
                             float* __restrict__ dpred, int64_t B, int kind, float invB) {
@@ -290,6 +360,12 @@ int krs_dense_fwd(const float* x, const float* W, const float* b, int act, float
                   void* stream) {
   KRS_REQUIRE(x && W && y, "krs_dense_fwd: null argument");
   KRS_REQUIRE(act >= KRS_ACT_LINEAR && act <= KRS_ACT_SWISH, "krs_dense_fwd: unknown activation %d", act);
+  if (N <= 8 && B > 0) {
+    const unsigned grid = (unsigned)krs::imax<int64_t>(1, krs::imin<int64_t>(ceil_div<int64_t>(B, 8), (int64_t)sm_count() * 16));
+    dense_skinny_fwd_kernel<8><<<grid, 256, 0, as_stream(stream)>>>(x, W, b, y, B, K, N, act);
+    KRS_LAUNCH_CHECK();
+    return KRS_OK;
+  }
   Epilogue e;
   e.kind = EPI_BIAS_ACT;
   e.bias = b;
@@ -318,6 +394,19 @@ int krs_dense_bwd(const float* gy, const float* x, const float* W, const float* 
     int rc = launch_prep(1, gy, nullptr, act == KRS_ACT_LINEAR ? nullptr : y, nullptr, dz, nullptr, db, B, N, act, 0, s);
     if (rc) return rc;
     dzp = dz;
+  }
+  if (N <= 8) {
+    KRS_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)K * N, s));
+    const int rows_per_block = 128;
+    dense_skinny_dw_kernel<8><<<(unsigned)ceil_div<int64_t>(B, rows_per_block), 256, 0, s>>>(x, dzp, dW, B, K, N, rows_per_block);
+    KRS_LAUNCH_CHECK();
+    if (dx) {
+      const int64_t total = B * (int64_t)K;
+      dense_skinny_dx_kernel<8><<<(unsigned)krs::imax<int64_t>(1, krs::imin<int64_t>(ceil_div<int64_t>(total, 256), (int64_t)sm_count() * 32)),
+                                  256, 0, s>>>(dzp, W, dx, B, K, N);
+      KRS_LAUNCH_CHECK();
+    }
+    return KRS_OK;
   }
   Epilogue none;
   int rc = gemm(x, K, true, dzp, N, false, dW, N, K, N, B, none, pick_split_k(K, N, B), false, s);   // dW = x^T dz
