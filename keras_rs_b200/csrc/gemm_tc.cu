@@ -45,7 +45,7 @@ namespace {
 
 constexpr int BM = 128;          // rows per tile == TMEM lanes
 constexpr int BK = 16;           // fp32 elements per k-block (64 B)
-constexpr int STAGES = 4;
+constexpr int MAX_STAGES = 12;    // ring depth is chosen per launch from the shared-memory budget
 constexpr int MAX_BN = 256;
 constexpr int NUM_THREADS = 320;
 constexpr int A_BYTES = BM * BK * 4;             // 8192
@@ -59,6 +59,7 @@ struct TcArgs {
   int64_t ldc;
   int64_t M, N, K;
   int bn;                 // N tile (multiple of 16, <= 256)
+  int stages;             // shared-memory ring depth (3..MAX_STAGES)
   int tiles_m, tiles_n, splits;
   int64_t kblocks_total;  // ceil(K / BK)
   int64_t kblocks_per_split;
@@ -284,13 +285,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int b_bytes = g.bn * BK * 4;
   const int raw_bytes = A_BYTES + b_bytes;
   const int stage_bytes = 2 * raw_bytes;
+  const int STAGES = g.stages;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * stage_bytes);
-  uint64_t* full_bar = bars;                 // [STAGES] TMA landed
-  uint64_t* conv_bar = bars + STAGES;        // [STAGES] hi/lo tiles ready
-  uint64_t* empty_bar = bars + 2 * STAGES;   // [STAGES] MMAs that read the stage have completed
-  uint64_t* tmem_full = bars + 3 * STAGES;   // [2]
-  uint64_t* tmem_empty = bars + 3 * STAGES + 2;  // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
+  uint64_t* full_bar = bars;                     // [STAGES] TMA landed
+  uint64_t* conv_bar = bars + MAX_STAGES;        // [STAGES] hi/lo tiles ready
+  uint64_t* empty_bar = bars + 2 * MAX_STAGES;   // [STAGES] MMAs that read the stage have completed
+  uint64_t* tmem_full = bars + 3 * MAX_STAGES;   // [1]
+  uint64_t* tmem_empty = bars + 3 * MAX_STAGES + 2;  // [1]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -333,9 +335,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int64_t kb0 = (int64_t)split * g.kblocks_per_split;
       const int64_t kb1 = imin<int64_t>(g.kblocks_total, kb0 + g.kblocks_per_split);
       for (int64_t kb = kb0; kb < kb1; ++kb) {
-        mbar_wait_relaxed(&empty_bar[stage], phase ^ 1);
+        // critical path: lane 0 polls without sleeping (a sleeping producer added microseconds per stage
+        // round trip), the other lanes park at the warp barrier
+        if (lane == 0) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], (uint32_t)raw_bytes);
+        }
         unsigned char* st = smem + (size_t)stage * stage_bytes;
-        if (lane == 0) mbar_expect_tx(&full_bar[stage], (uint32_t)raw_bytes);
         __syncwarp();
         const int k0 = (int)(kb * BK);
         if (lane < nA) {
@@ -518,7 +524,7 @@ bool make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, i
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
 
@@ -566,7 +572,9 @@ int gemm_tc(const float* A, int64_t lda, bool transA, const float* B, int64_t ld
     g.epi_vec = ((ldc % 4) == 0 && aligned16(C) && ok16(epi.x0) && ok16(epi.x) && ok16(epi.h2_out) && ok16(epi.z_out) &&
                  ok16(epi.add1) && ok16(epi.add2) && (g.bn % 16) == 0 && ((int64_t)g.bn % 4) == 0) ? 1 : 0;
   }
-  g.no_mask = 0;
+  // the tensor core ignores the low 13 mantissa bits of a tf32 operand: leaving hi = raw fp32 is bit-identical
+  // to masking it (tests/tc_stress.py, both modes) and saves a third of the converter's shared-memory stores
+  g.no_mask = 1;
   if (const char* e = getenv("KRS_TC_NO_MASK")) g.no_mask = atoi(e);
   g.mn_lbo = 2048; g.mn_sbo = 512; g.mn_kstep = 1024; g.mn_layout = 1;
   int mn_swz = (int)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
@@ -589,7 +597,10 @@ int gemm_tc(const float* A, int64_t lda, bool transA, const float* B, int64_t ld
     KRS_CUDA(cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, stream));
 
   const size_t stage_bytes = 2 * (size_t)(A_BYTES + g.bn * BK * 4);
-  const size_t smem = 1024 + STAGES * stage_bytes + 256;
+  const size_t budget = 227 * 1024 - 1024 - 512;                    // alignment slack + barriers
+  g.stages = (int)imin<int64_t>(MAX_STAGES, (int64_t)(budget / stage_bytes));
+  if (g.stages < 3) return KRS_EUNSUPPORTED;
+  const size_t smem = 1024 + g.stages * stage_bytes + 512;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {

@@ -197,16 +197,24 @@ def feature_cross(x0: np.ndarray, x: np.ndarray | None, V: np.ndarray, b: np.nda
     return x0 * a + x                              # :194
 
 
-def feature_cross_bwd(gy, x0, x, V, b=None, U=None, diag_scale=0.0, pre_activation=None):
+def feature_cross_bwd(gy, x0, x, V, b=None, U=None, diag_scale=0.0, pre_activation=None, z_for_grad=None):
     """Analytic backward of feature_cross.  Returns dict dx0, dx, dV, db, dU.
-    x0 and x are treated as independent inputs (caller sums when they are the same tensor)."""
+    x0 and x are treated as independent inputs (caller sums when they are the same tensor).
+    z_for_grad: optional pre-activation at which the activation DERIVATIVE is evaluated.  relu'(z) is
+    discontinuous at 0, so a checker comparing against an implementation whose z differs in the last
+    ulp must take the derivative mask from that implementation's own z (otherwise one flipped element
+    near z = 0 changes whole rows of the gradients)."""
     h = x if U is None else x @ U
     z = h @ V + (0 if b is None else b)
     a = activation(pre_activation, z)
     h2 = a + (F32(diag_scale) * x if diag_scale else 0)
     dh2 = gy * x0
     dx0 = gy * h2
-    dz = dh2 * activation_grad(pre_activation, z, a)
+    if z_for_grad is not None:
+        zg = np.asarray(z_for_grad, dtype=z.dtype)
+        dz = dh2 * activation_grad(pre_activation, zg, activation(pre_activation, zg))
+    else:
+        dz = dh2 * activation_grad(pre_activation, z, a)
     dV = h.T @ dz
     db = dz.sum(axis=0)
     dh = dz @ V.T

@@ -269,7 +269,10 @@ def test_feature_cross_fwd_bwd_vs_oracle(K, P, act, diag, same):
     assert_close(npy(y), ref, what="cross fwd")
     gy = rng.normal(size=(B, D)).astype(np.float32)
     y.backward(dev(gy))
-    r = O.feature_cross_bwd(gy, x0, x, V, b, U, diag, act)
+    # derivative mask from the kernel's own pre-activation (relu' is discontinuous at 0)
+    hz = dev(x) if P is None else K.ops.linear_no_bias(dev(x), layer.down_proj_kernel.detach())
+    z_gpu = npy(K.ops.dense(hz.contiguous(), layer.kernel.detach(), layer.bias.detach(), 0))
+    r = O.feature_cross_bwd(gy, x0, x, V, b, U, diag, act, z_for_grad=z_gpu)
     if same:
         assert_close(npy(tx0.grad), r["dx0"] + r["dx"], what="dx total")
     else:

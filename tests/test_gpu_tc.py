@@ -71,7 +71,9 @@ def test_tc_feature_cross_vs_oracle(tc, P, act):
     assert_close(npy(y), ref, what="tc cross fwd")
     gy = rng.normal(size=(B, D)).astype(np.float32)
     y.backward(dev(gy))
-    r = O.feature_cross_bwd(f64(gy), f64(x0), f64(x), f64(V), f64(b), f64(U), 0.25, act)
+    hz = dev(x) if P is None else tc.ops.linear_no_bias(dev(x), layer.down_proj_kernel.detach())
+    z_gpu = npy(tc.ops.dense(hz.contiguous(), layer.kernel.detach(), layer.bias.detach(), 0))
+    r = O.feature_cross_bwd(f64(gy), f64(x0), f64(x), f64(V), f64(b), f64(U), 0.25, act, z_for_grad=z_gpu)
     assert_close(npy(tx0.grad), r["dx0"], what="tc dx0")
     assert_close(npy(tx.grad), r["dx"], what="tc dx")
     assert_close(npy(layer.kernel.grad), r["dV"], what="tc dV")
