@@ -197,13 +197,16 @@ __device__ __forceinline__ const float* epi_stream2(const Epilogue& e) {
 __device__ __forceinline__ void aux_prefetch(const float* p, int64_t off, bool ok, Aux16& a) {
   if (p != nullptr && ok) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) a.v[q] = *reinterpret_cast<const float4*>(p + off + 4 * q);
+    for (int q = 0; q < 4; ++q) a.v[q] = __ldg(reinterpret_cast<const float4*>(p + off + 4 * q));
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) a.v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 
 // full: the chunk is 16 in-range columns with 16-byte aligned rows (aux streams were prefetched)
 __device__ __forceinline__ void epilogue_row16(const TcArgs& g, int64_t m, int64_t n0, const uint32_t (&acc)[16], bool full,
-                                               const Aux16& a1, const Aux16& a2) {
+                                               const Aux16& a1, const Aux16& a2, const Aux16& bia) {
   const Epilogue& e = g.epi;
   const int64_t off = m * g.ldc + n0;
   const int cnt = (int)imin<int64_t>(16, g.N - n0);
@@ -222,7 +225,7 @@ __device__ __forceinline__ void epilogue_row16(const TcArgs& g, int64_t m, int64
   }
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    float v[4], out[4], h2v[4], zv[4], s1[4], s2[4];
+    float v[4], out[4], h2v[4], zv[4], s1[4], s2[4], bv[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) v[j] = __uint_as_float(acc[q * 4 + j]);
     const int64_t o = off + q * 4;
@@ -234,19 +237,21 @@ __device__ __forceinline__ void epilogue_row16(const TcArgs& g, int64_t m, int64
     if (full) {
       s1[0] = a1.v[q].x; s1[1] = a1.v[q].y; s1[2] = a1.v[q].z; s1[3] = a1.v[q].w;
       s2[0] = a2.v[q].x; s2[1] = a2.v[q].y; s2[2] = a2.v[q].z; s2[3] = a2.v[q].w;
+      bv[0] = bia.v[q].x; bv[1] = bia.v[q].y; bv[2] = bia.v[q].z; bv[3] = bia.v[q].w;
     } else {
       for (int j = 0; j < c4; ++j) {
         s1[j] = p1 ? p1[o + j] : 0.f;
         s2[j] = p2 ? p2[o + j] : 0.f;
+        bv[j] = e.bias ? e.bias[n + j] : 0.f;
       }
     }
     if (e.kind == EPI_NONE) {
       for (int j = 0; j < c4; ++j) out[j] = v[j] + (g.accumulate ? g.C[o + j] : 0.f);
     } else if (e.kind == EPI_BIAS_ACT) {
-      for (int j = 0; j < c4; ++j) out[j] = act_apply(e.act, v[j] + (e.bias ? e.bias[n + j] : 0.f));
+      for (int j = 0; j < c4; ++j) out[j] = act_apply(e.act, v[j] + bv[j]);
     } else if (e.kind == EPI_CROSS) {
       for (int j = 0; j < c4; ++j) {
-        const float z = v[j] + (e.bias ? e.bias[n + j] : 0.f);
+        const float z = v[j] + bv[j];
         const float a = act_apply(e.act, z);
         const float h2 = (e.diag != 0.f) ? a + e.diag * s2[j] : a;
         zv[j] = z;
@@ -461,7 +466,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const float* p2 = epi_stream2(g.epi);
       const int64_t nbase = (int64_t)tn * g.bn;
       auto chunk_full = [&](int c) { return g.epi_vec && m < g.M && (nbase + c + 16) <= g.N; };
-      Aux16 a1, a2, b1, b2;
+      Aux16 a1, a2, b1, b2, bi;
       // first chunk's operands are requested BEFORE waiting for the accumulator
       aux_prefetch(p1, m * g.ldc + nbase, chunk_full(0), a1);
       aux_prefetch(p2, m * g.ldc + nbase, chunk_full(0), a2);
@@ -474,6 +479,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           aux_prefetch(p1, m * g.ldc + nbase + c + 16, chunk_full(c + 16), b1);
           aux_prefetch(p2, m * g.ldc + nbase + c + 16, chunk_full(c + 16), b2);
         }
+        // bias chunk: same 64 bytes for every row -> read-only path, L1 resident after the first touch;
+        // issued before the TMEM loads so its latency overlaps them
+        aux_prefetch(g.epi.bias, nbase + c, chunk_full(c), bi);
         uint32_t r[16], r2[16];
         tc_ld16(t_row + (uint32_t)c, r);
         tc_ld16(t_row + (uint32_t)(MAX_BN + c), r2);
@@ -482,7 +490,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int j = 0; j < 16; ++j)
           r[j] = empty_k ? 0u : __float_as_uint(__fadd_rn(__uint_as_float(r[j]), __uint_as_float(r2[j])));
         const int64_t n0 = nbase + c;
-        if (m < g.M && n0 < g.N) epilogue_row16(g, m, n0, r, chunk_full(c), a1, a2);
+        if (m < g.M && n0 < g.N) epilogue_row16(g, m, n0, r, chunk_full(c), a1, a2, bi);
         a1 = b1;
         a2 = b2;
       }
@@ -570,7 +578,7 @@ int gemm_tc(const float* A, int64_t lda, bool transA, const float* B, int64_t ld
   {
     auto ok16 = [](const void* q) { return q == nullptr || aligned16(q); };
     g.epi_vec = ((ldc % 4) == 0 && aligned16(C) && ok16(epi.x0) && ok16(epi.x) && ok16(epi.h2_out) && ok16(epi.z_out) &&
-                 ok16(epi.add1) && ok16(epi.add2) && (g.bn % 16) == 0 && ((int64_t)g.bn % 4) == 0) ? 1 : 0;
+                 ok16(epi.add1) && ok16(epi.add2) && ok16(epi.bias) && (g.bn % 16) == 0 && ((int64_t)g.bn % 4) == 0) ? 1 : 0;
   }
   // the tensor core ignores the low 13 mantissa bits of a tf32 operand: leaving hi = raw fp32 is bit-identical
   // to masking it (tests/tc_stress.py, both modes) and saves a third of the converter's shared-memory stores
