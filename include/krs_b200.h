@@ -45,6 +45,9 @@ int krs_get_gemm_engine(void);
 /* Number of tcgen05 GEMM launches so far in this process (tests use it to prove the tensor-pipe
  * kernel, not the FFMA fallback, produced a result). */
 long long krs_gemm_tc_launch_count(void);
+/* Debug: device buffer of >= 16001 uint64 receiving a per-role clock64 timeline of CTA 0 of subsequent
+ * tcgen05 GEMM launches ([0] = entry count, then (tag<<32|index, clock) pairs); NULL disables. */
+int krs_gemm_tc_set_trace(void* dev_buf);
 
 /* ------------------------------------------------------------------ activations
  * keras.activations used as FeatureCross.pre_activation / Dense.activation

@@ -53,6 +53,7 @@ constexpr int KC_MAX = 1024;                     // max K elements accumulated i
 constexpr int SPIN_LIMIT = 1 << 26;              // turns a protocol bug into a trap instead of a hang
 
 std::atomic<long long> g_tc_launches{0};
+std::atomic<unsigned long long*> g_trace{nullptr};
 
 struct TcArgs {
   float* C;
@@ -65,11 +66,23 @@ struct TcArgs {
   int64_t kblocks_per_split;
   int a_mn_major, b_mn_major;
   int atomic_out, accumulate;
+  unsigned long long* trace;   // debug: (tag, clock) pairs from CTA 0 (nullptr normally)
   int epi_vec;            // rows of C / h2 / z / aux streams are 16-byte aligned (vector epilogue)
   int no_mask;            // 1: leave hi = raw fp32 bits (hardware ignores the low 13 mantissa bits)
   int mn_lbo, mn_sbo, mn_kstep, mn_layout;   // MN-major descriptor strides (bytes) and UMMA layout type
   Epilogue epi;
 };
+
+// debug timeline: trace[0] = entry counter, then (tag, clock64) pairs; CTA 0 only
+__device__ __forceinline__ void trace_ev(const unsigned long long* tr_c, unsigned tag, unsigned idx) {
+  unsigned long long* tr = const_cast<unsigned long long*>(tr_c);
+  if (tr == nullptr || blockIdx.x != 0) return;
+  const unsigned long long slot = atomicAdd(tr, 1ULL);
+  if (slot < 8000) {
+    tr[1 + 2 * slot] = ((unsigned long long)tag << 32) | idx;
+    tr[2 + 2 * slot] = (unsigned long long)clock64();
+  }
+}
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -358,6 +371,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           if (!g.b_mn_major) tma_load_2d(sb, &tmap_b, k0, tn * g.bn, &full_bar[stage]);                     // box {16 k, bn n}
           else tma_load_2d(sb + blk * 2048, &tmap_b, tn * g.bn + blk * 32, k0, &full_bar[stage]);
         }
+        if (lane == 0) trace_ev(g.trace, 1, (unsigned)kb);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -380,6 +394,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         mbar_wait(&conv_bar[stage], phase);
         tc_fence_after();
         if (lane == 0) {
+          trace_ev(g.trace, 4, (unsigned)kb);
           const uint32_t a_hi = smem_u32(smem + (size_t)stage * stage_bytes);
           const uint32_t b_hi = a_hi + A_BYTES;
           const uint32_t a_lo = a_hi + raw_bytes;
@@ -397,6 +412,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
           tc_commit(&empty_bar[stage]);                       // frees the stage when these MMAs retire
           if (kb == kb1 - 1) tc_commit(&tmem_full[0]);        // accumulators complete
+          trace_ev(g.trace, 5, (unsigned)kb);
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -416,6 +432,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int64_t kb1 = imin<int64_t>(g.kblocks_total, kb0 + g.kblocks_per_split);
       for (int64_t kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase);
+        if (ct == 0) trace_ev(g.trace, 2, (unsigned)kb);
         float4* raw = reinterpret_cast<float4*>(smem + (size_t)stage * stage_bytes);
         float4* lo = reinterpret_cast<float4*>(smem + (size_t)stage * stage_bytes + raw_bytes);
         // all loads first (<= 12 float4 per thread at bn = 256), then split + store: one shared-memory
@@ -449,6 +466,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(&conv_bar[stage]);
+        if (ct == 0) trace_ev(g.trace, 3, (unsigned)kb);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -472,6 +490,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       aux_prefetch(p2, m * g.ldc + nbase, chunk_full(0), a2);
       mbar_wait_relaxed(&tmem_full[0], acc_phase);
       tc_fence_after();
+      if (warp == 2 && lane == 0) trace_ev(g.trace, 6, (unsigned)tile);
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16);
       const bool empty_k = ((int64_t)split * g.kblocks_per_split) >= g.kblocks_total;
       for (int c = 0; c < g.bn; c += 16) {
@@ -497,6 +516,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[0]);
+      if (warp == 2 && lane == 0) trace_ev(g.trace, 7, (unsigned)tile);
       acc_phase ^= 1;
     }
   }
@@ -582,6 +602,7 @@ int gemm_tc(const float* A, int64_t lda, bool transA, const float* B, int64_t ld
   }
   // the tensor core ignores the low 13 mantissa bits of a tf32 operand: leaving hi = raw fp32 is bit-identical
   // to masking it (tests/tc_stress.py, both modes) and saves a third of the converter's shared-memory stores
+  g.trace = g_trace.load();
   g.no_mask = 1;
   if (const char* e = getenv("KRS_TC_NO_MASK")) g.no_mask = atoi(e);
   g.mn_lbo = 2048; g.mn_sbo = 512; g.mn_kstep = 1024; g.mn_layout = 1;
@@ -623,6 +644,11 @@ int gemm_tc(const float* A, int64_t lda, bool transA, const float* B, int64_t ld
   return KRS_OK;
 }
 
+void gemm_tc_set_trace(unsigned long long* p) { g_trace.store(p); }
 }  // namespace krs
 
 extern "C" long long krs_gemm_tc_launch_count(void) { return krs::gemm_tc_launches(); }
+extern "C" int krs_gemm_tc_set_trace(void* dev_buf) {
+  krs::gemm_tc_set_trace(reinterpret_cast<unsigned long long*>(dev_buf));
+  return KRS_OK;
+}
