@@ -65,6 +65,7 @@ struct TcArgs {
   int64_t kblocks_total;  // ceil(K / BK)
   int64_t kblocks_per_split;
   int a_mn_major, b_mn_major;
+  int a_3d, b_3d;         // MN-major operand loaded by ONE 3-D box {32, BK, blocks} per k-block
   int atomic_out, accumulate;
   unsigned long long* trace;   // debug: (tag, clock) pairs from CTA 0 (nullptr normally)
   int epi_vec;            // rows of C / h2 / z / aux streams are 16-byte aligned (vector epilogue)
@@ -140,6 +141,13 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
           smem_u32(smem_dst)),
       "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
       : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -343,8 +351,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // (1 per K-major operand, bn/32 or 4 per MN-major operand) are issued by different lanes in parallel
     int stage = 0;
     uint32_t phase = 0;
-    const int nA = g.a_mn_major ? BM / 32 : 1;
-    const int nB = g.b_mn_major ? g.bn / 32 : 1;
+    const int nA = (g.a_mn_major && !g.a_3d) ? BM / 32 : 1;
+    const int nB = (g.b_mn_major && !g.b_3d) ? g.bn / 32 : 1;
     for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int split = (int)(tile / tiles_mn);
       const int64_t rem = tile - (int64_t)split * tiles_mn;
@@ -364,11 +372,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int k0 = (int)(kb * BK);
         if (lane < nA) {
           if (!g.a_mn_major) tma_load_2d(st, &tmap_a, k0, tm * BM, &full_bar[stage]);                       // box {16 k, 128 m}
+          else if (g.a_3d) tma_load_3d(st, &tmap_a, 0, k0, tm * (BM / 32), &full_bar[stage]);              // box {32 m, 16 k, 4}
           else tma_load_2d(st + lane * 2048, &tmap_a, tm * BM + lane * 32, k0, &full_bar[stage]);          // box {32 m, 16 k}
         } else if (lane < nA + nB) {
           const int blk = lane - nA;
           unsigned char* sb = st + A_BYTES;
           if (!g.b_mn_major) tma_load_2d(sb, &tmap_b, k0, tn * g.bn, &full_bar[stage]);                     // box {16 k, bn n}
+          else if (g.b_3d) tma_load_3d(sb, &tmap_b, 0, k0, tn * (g.bn / 32), &full_bar[stage]);            // box {32 n, 16 k, bn/32}
           else tma_load_2d(sb + blk * 2048, &tmap_b, tn * g.bn + blk * 32, k0, &full_bar[stage]);
         }
         if (lane == 0) trace_ev(g.trace, 1, (unsigned)kb);
@@ -462,8 +472,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             lo[i] = l;
           }
         }
+        if (ct == 0) trace_ev(g.trace, 8, (unsigned)kb);
         // generic-proxy writes must be visible to the tensor core (async proxy) before the MMA reads them
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (ct == 0) trace_ev(g.trace, 9, (unsigned)kb);
         __syncwarp();
         if (lane == 0) mbar_arrive(&conv_bar[stage]);
         if (ct == 0) trace_ev(g.trace, 3, (unsigned)kb);
@@ -556,6 +568,20 @@ bool make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, i
   return r == CUDA_SUCCESS;
 }
 
+// MN-contiguous matrix [rows = K][cols = MN] viewed as 3-D {32, K, MN/32}: one box {32, BK, blocks} lands in
+// shared memory as `blocks` consecutive [BK rows x 128 B] sub-tiles — exactly the MN-major UMMA layout.
+bool make_map_3d(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int blocks, CUtensorMapSwizzle swz) {
+  auto fn = encode_fn();
+  if (!fn || (cols % 32) != 0) return false;
+  cuuint64_t dims[3] = {32, (cuuint64_t)rows, (cuuint64_t)(cols / 32)};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * sizeof(float), 128};
+  cuuint32_t box[3] = {32, (cuuint32_t)BK, (cuuint32_t)blocks};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 int pick_bn(int64_t N, bool b_mn_major) {
   const int gran = b_mn_major ? 32 : 16;
   const int64_t tiles = ceil_div<int64_t>(N, MAX_BN);
@@ -615,11 +641,21 @@ int gemm_tc(const float* A, int64_t lda, bool transA, const float* B, int64_t ld
 
   CUtensorMap ma, mb;
   bool ok;
+  g.a_3d = g.b_3d = 0;
+  const bool allow3d = getenv("KRS_TC_NO_3D") == nullptr;
   if (!g.a_mn_major) ok = make_map(&ma, A, M, K, lda, BK, BM, CU_TENSOR_MAP_SWIZZLE_64B);        // [M][K]
-  else ok = make_map(&ma, A, K, M, lda, 32, BK, (CUtensorMapSwizzle)mn_swz);                     // [K][M]
+  else {
+    ok = allow3d && make_map_3d(&ma, A, K, M, lda, BM / 32, (CUtensorMapSwizzle)mn_swz);
+    if (ok) g.a_3d = 1;
+    else ok = make_map(&ma, A, K, M, lda, 32, BK, (CUtensorMapSwizzle)mn_swz);                   // [K][M]
+  }
   if (!ok) return KRS_EUNSUPPORTED;
   if (!g.b_mn_major) ok = make_map(&mb, B, N, K, ldb, BK, g.bn, CU_TENSOR_MAP_SWIZZLE_64B);      // [N][K]
-  else ok = make_map(&mb, B, K, N, ldb, 32, BK, (CUtensorMapSwizzle)mn_swz);                     // [K][N]
+  else {
+    ok = allow3d && make_map_3d(&mb, B, K, N, ldb, g.bn / 32, (CUtensorMapSwizzle)mn_swz);
+    if (ok) g.b_3d = 1;
+    else ok = make_map(&mb, B, K, N, ldb, 32, BK, (CUtensorMapSwizzle)mn_swz);                   // [K][N]
+  }
   if (!ok) return KRS_EUNSUPPORTED;
 
   if (g.atomic_out && !accumulate)

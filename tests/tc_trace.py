@@ -20,7 +20,7 @@ lib.krs_gemm_tc_set_trace(None)
 t = tr.cpu().numpy()
 n = int(t[0]); ev = [(int(t[1+2*i]) >> 32, int(t[1+2*i]) & 0xffffffff, int(t[2+2*i])) for i in range(min(n, 8000))]
 ev.sort(key=lambda e: e[2]); t0 = ev[0][2]
-names = {1: "TMA issued", 2: "conv saw full", 3: "conv done", 4: "mma saw conv", 5: "mma committed", 6: "epi start", 7: "epi done"}
+names = {8: "conv stores issued", 9: "conv fence done", 1: "TMA issued", 2: "conv saw full", 3: "conv done", 4: "mma saw conv", 5: "mma committed", 6: "epi start", 7: "epi done"}
 print("entries", n)
 by = {k: [(i, c - t0) for tag, i, c in ev if tag == k] for k in names}
 for k in (6, 7):
@@ -30,6 +30,9 @@ for tile in (0, 1, 2):
     lo, hi = tile * 52, tile * 52 + 52
     def seq(k): return [c for (i, c) in by[k][lo:hi]]
     s1, s2, s3, s4, s5 = seq(1), seq(2), seq(3), seq(4), seq(5)
+    s8, s9 = seq(8), seq(9)
+    if len(s8) == 52:
+        print(f"   conv breakdown: full->stores issued {np.median(np.array(s8)-np.array(s2)):.0f}; stores->fence done {np.median(np.array(s9)-np.array(s8)):.0f}; fence->arrive {np.median(np.array(s3)-np.array(s9)):.0f}")
     if len(s5) < 52: break
     d = lambda a: np.diff(np.array(a))
     print(f"tile {tile}: mainloop {s5[-1]-s4[0]} clks; per-kb period mma-committed median {np.median(d(s5)):.0f}; TMA-issue period {np.median(d(s1)):.0f}; "
