@@ -9,12 +9,12 @@
 // (the dropped lo·lo term is ~2^-22 relative), which keeps results within ~1e-6 of an fp32 matmul —
 // inside the 1e-5 bar of the north star, which a single-pass TF32 product (1e-3) would miss.
 //
-// Structure (one CTA per SM, persistent over output tiles, 320 threads):
+// Structure (one CTA per SM, persistent over output tiles, 448 threads):
 //   warp 0      TMA producer: cp.async.bulk.tensor fp32 tiles global -> shared (mbarrier complete_tx)
 //   warp 1      MMA issuer: one elected lane issues tcgen05.mma.kind::tf32 (SS operands, D in TMEM),
 //               tcgen05.commit releases shared-memory stages / publishes the accumulator
 //   warps 2-5   epilogue: tcgen05.ld accumulator rows -> registers -> fused epilogue -> global
-//   warps 6-9   converters: shared -> registers -> shared, write hi (in place) and lo tiles (highest
+//   warps 6-13  converters: shared -> registers -> shared, write hi (in place) and lo tiles (highest
 //               warp ids: the scheduler arbitrates highest-warp-id first and they are the critical stage)
 // Shared memory ring: 4 stages x (A_raw | B_raw | A_lo | B_lo), BK = 16 floats per stage.
 // TMEM: 512 columns = TWO accumulators x 256 columns (128 lanes = the 128 rows of the tile): the hi·hi
@@ -47,7 +47,10 @@ constexpr int BM = 128;          // rows per tile == TMEM lanes
 constexpr int BK = 16;           // fp32 elements per k-block (64 B)
 constexpr int MAX_STAGES = 12;    // ring depth is chosen per launch from the shared-memory budget
 constexpr int MAX_BN = 256;
-constexpr int NUM_THREADS = 320;
+constexpr int NUM_THREADS = 448;          // TMA, MMA, 4 epilogue warps, 8 converter warps
+constexpr int NUM_CONV_THREADS = 256;
+constexpr int EPI_LD = 36;                // staging row pitch in floats (32 + 4: conflict-free 16-byte accesses)
+constexpr int EPI_SMEM_BYTES = 4 * 32 * EPI_LD * 4;   // one 32x32 staging tile per epilogue warp
 constexpr int A_BYTES = BM * BK * 4;             // 8192
 constexpr int KC_MAX = 1024;                     // max K elements accumulated inside one TMEM tile
 constexpr int SPIN_LIMIT = 1 << 26;              // turns a protocol bug into a trap instead of a hang
@@ -74,15 +77,14 @@ struct TcArgs {
   Epilogue epi;
 };
 
-// debug timeline: trace[0] = entry counter, then (tag, clock64) pairs; CTA 0 only
-__device__ __forceinline__ void trace_ev(const unsigned long long* tr_c, unsigned tag, unsigned idx) {
+// debug timeline (CTA 0 only): four role-private regions of 2000 (tag, clock64) pairs written with plain
+// stores — a returning atomic would stall the traced thread for ~700 clocks per event and distort the timeline
+__device__ __forceinline__ void trace_ev(const unsigned long long* tr_c, int role, int& count, unsigned tag, unsigned idx) {
   unsigned long long* tr = const_cast<unsigned long long*>(tr_c);
-  if (tr == nullptr || blockIdx.x != 0) return;
-  const unsigned long long slot = atomicAdd(tr, 1ULL);
-  if (slot < 8000) {
-    tr[1 + 2 * slot] = ((unsigned long long)tag << 32) | idx;
-    tr[2 + 2 * slot] = (unsigned long long)clock64();
-  }
+  if (tr == nullptr || blockIdx.x != 0 || count >= 2000) return;
+  tr[1 + role * 4000 + 2 * count] = ((unsigned long long)tag << 32) | idx;
+  tr[2 + role * 4000 + 2 * count] = (unsigned long long)clock64();
+  ++count;
 }
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -202,102 +204,78 @@ __device__ __forceinline__ float tf32_rna_f(float x) {
   return __uint_as_float(r);
 }
 
-// ---------------------------------------------------------------- fused epilogue on 16 columns of one row
-// The two per-element operand streams of the epilogue (CROSS: x0, x ; ADD2: add1, add2) are prefetched
-// one 16-column chunk ahead by the caller (Aux16), so their global-memory latency overlaps the TMEM
-// loads and the arithmetic of the previous chunk instead of sitting on the critical path.
-struct Aux16 {
-  float4 v[4];
-};
+// ---------------------------------------------------------------- fused epilogue on one float4 (4 columns of one row)
+// Called AFTER the accumulator chunk has been transposed through shared memory, so that a warp instruction
+// touches 4 rows x 128 contiguous bytes (4 cache lines) instead of 32 rows x 16 bytes (32 lines): the first
+// version's row-per-thread epilogue spent 5.6K clocks per 16-column chunk in the LSU (tests/tc_trace.py).
 __device__ __forceinline__ const float* epi_stream1(const Epilogue& e) {
   return e.kind == EPI_CROSS ? e.x0 : (e.kind == EPI_ADD2 ? e.add1 : nullptr);
 }
 __device__ __forceinline__ const float* epi_stream2(const Epilogue& e) {
   return e.kind == EPI_CROSS ? e.x : (e.kind == EPI_ADD2 ? e.add2 : nullptr);
 }
-__device__ __forceinline__ void aux_prefetch(const float* p, int64_t off, bool ok, Aux16& a) {
-  if (p != nullptr && ok) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) a.v[q] = __ldg(reinterpret_cast<const float4*>(p + off + 4 * q));
-  } else {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) a.v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-}
-
-// full: the chunk is 16 in-range columns with 16-byte aligned rows (aux streams were prefetched)
-__device__ __forceinline__ void epilogue_row16(const TcArgs& g, int64_t m, int64_t n0, const uint32_t (&acc)[16], bool full,
-                                               const Aux16& a1, const Aux16& a2, const Aux16& bia) {
+// vec path: n..n+3 in range, all pointers 16-byte aligned
+__device__ __forceinline__ void epilogue_f4(const TcArgs& g, int64_t m, int64_t n, float4 acc, float4 s1, float4 s2, float4 bv) {
   const Epilogue& e = g.epi;
-  const int64_t off = m * g.ldc + n0;
-  const int cnt = (int)imin<int64_t>(16, g.N - n0);
-  if (cnt <= 0) return;
+  const int64_t o = m * g.ldc + n;
   if (g.atomic_out) {
-    if (full) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q)   // 16-byte vector reductions (RED.E.ADD.F32x4), round-to-nearest in L2
-        atomicAdd(reinterpret_cast<float4*>(g.C + off + 4 * q),
-                  make_float4(__uint_as_float(acc[4 * q]), __uint_as_float(acc[4 * q + 1]), __uint_as_float(acc[4 * q + 2]),
-                              __uint_as_float(acc[4 * q + 3])));
-    } else {
-      for (int j = 0; j < cnt; ++j) atomicAdd(g.C + off + j, __uint_as_float(acc[j]));
-    }
+    atomicAdd(reinterpret_cast<float4*>(g.C + o), acc);          // RED.E.ADD.F32x4, round-to-nearest in L2
     return;
   }
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    float v[4], out[4], h2v[4], zv[4], s1[4], s2[4], bv[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] = __uint_as_float(acc[q * 4 + j]);
-    const int64_t o = off + q * 4;
-    const int64_t n = n0 + q * 4;
-    const int c4 = full ? 4 : (int)imax<int64_t>(0, imin<int64_t>(4, g.N - n));
-    if (c4 <= 0) break;
-    const float* p1 = epi_stream1(e);
-    const float* p2 = epi_stream2(e);
-    if (full) {
-      s1[0] = a1.v[q].x; s1[1] = a1.v[q].y; s1[2] = a1.v[q].z; s1[3] = a1.v[q].w;
-      s2[0] = a2.v[q].x; s2[1] = a2.v[q].y; s2[2] = a2.v[q].z; s2[3] = a2.v[q].w;
-      bv[0] = bia.v[q].x; bv[1] = bia.v[q].y; bv[2] = bia.v[q].z; bv[3] = bia.v[q].w;
+  float v[4] = {acc.x, acc.y, acc.z, acc.w};
+  const float a1[4] = {s1.x, s1.y, s1.z, s1.w};
+  const float a2[4] = {s2.x, s2.y, s2.z, s2.w};
+  const float b[4] = {bv.x, bv.y, bv.z, bv.w};
+  float out[4], h2v[4], zv[4];
+  if (e.kind == EPI_NONE) {
+    if (g.accumulate) {
+      const float4 c = *reinterpret_cast<const float4*>(g.C + o);
+      out[0] = v[0] + c.x; out[1] = v[1] + c.y; out[2] = v[2] + c.z; out[3] = v[3] + c.w;
     } else {
-      for (int j = 0; j < c4; ++j) {
-        s1[j] = p1 ? p1[o + j] : 0.f;
-        s2[j] = p2 ? p2[o + j] : 0.f;
-        bv[j] = e.bias ? e.bias[n + j] : 0.f;
-      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) out[j] = v[j];
     }
-    if (e.kind == EPI_NONE) {
-      for (int j = 0; j < c4; ++j) out[j] = v[j] + (g.accumulate ? g.C[o + j] : 0.f);
-    } else if (e.kind == EPI_BIAS_ACT) {
-      for (int j = 0; j < c4; ++j) out[j] = act_apply(e.act, v[j] + bv[j]);
-    } else if (e.kind == EPI_CROSS) {
-      for (int j = 0; j < c4; ++j) {
-        const float z = v[j] + bv[j];
-        const float a = act_apply(e.act, z);
-        const float h2 = (e.diag != 0.f) ? a + e.diag * s2[j] : a;
-        zv[j] = z;
-        h2v[j] = h2;
-        out[j] = s1[j] * h2 + s2[j];                   // x0 * h2 + x  (feature_cross.py:194)
-      }
-      if (e.h2_out) {
-        if (full) *reinterpret_cast<float4*>(e.h2_out + o) = make_float4(h2v[0], h2v[1], h2v[2], h2v[3]);
-        else for (int j = 0; j < c4; ++j) e.h2_out[o + j] = h2v[j];
-      }
-      if (e.z_out) {
-        if (full) *reinterpret_cast<float4*>(e.z_out + o) = make_float4(zv[0], zv[1], zv[2], zv[3]);
-        else for (int j = 0; j < c4; ++j) e.z_out[o + j] = zv[j];
-      }
-    } else {  // EPI_ADD2
-      for (int j = 0; j < c4; ++j) {
-        float r = v[j];
-        if (p1) r += e.alpha1 * s1[j];
-        if (p2) r += e.alpha2 * s2[j];
-        out[j] = r;
-      }
+  } else if (e.kind == EPI_BIAS_ACT) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[j] = act_apply(e.act, v[j] + b[j]);
+  } else if (e.kind == EPI_CROSS) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float z = v[j] + b[j];
+      const float a = act_apply(e.act, z);
+      const float h2 = (e.diag != 0.f) ? a + e.diag * a2[j] : a;     // feature_cross.py:191-192
+      zv[j] = z;
+      h2v[j] = h2;
+      out[j] = a1[j] * h2 + a2[j];                                   // x0 * h2 + x   (feature_cross.py:194)
     }
-    if (full) *reinterpret_cast<float4*>(g.C + o) = make_float4(out[0], out[1], out[2], out[3]);
-    else for (int j = 0; j < c4; ++j) g.C[o + j] = out[j];
+    if (e.h2_out) *reinterpret_cast<float4*>(e.h2_out + o) = make_float4(h2v[0], h2v[1], h2v[2], h2v[3]);
+    if (e.z_out) *reinterpret_cast<float4*>(e.z_out + o) = make_float4(zv[0], zv[1], zv[2], zv[3]);
+  } else {  // EPI_ADD2
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[j] = v[j] + (e.add1 ? e.alpha1 * a1[j] : 0.f) + (e.add2 ? e.alpha2 * a2[j] : 0.f);
   }
+  *reinterpret_cast<float4*>(g.C + o) = make_float4(out[0], out[1], out[2], out[3]);
+}
+// scalar path for ragged / unaligned outputs
+__device__ __forceinline__ void epilogue_scalar(const TcArgs& g, int64_t m, int64_t n, float acc) {
+  const Epilogue& e = g.epi;
+  const int64_t o = m * g.ldc + n;
+  if (g.atomic_out) { atomicAdd(g.C + o, acc); return; }
+  const float* p1 = epi_stream1(e);
+  const float* p2 = epi_stream2(e);
+  const float s1 = p1 ? p1[o] : 0.f, s2 = p2 ? p2[o] : 0.f, b = e.bias ? e.bias[n] : 0.f;
+  float out;
+  if (e.kind == EPI_NONE) out = acc + (g.accumulate ? g.C[o] : 0.f);
+  else if (e.kind == EPI_BIAS_ACT) out = act_apply(e.act, acc + b);
+  else if (e.kind == EPI_CROSS) {
+    const float z = acc + b;
+    const float a = act_apply(e.act, z);
+    const float h2 = (e.diag != 0.f) ? a + e.diag * s2 : a;
+    if (e.h2_out) e.h2_out[o] = h2;
+    if (e.z_out) e.z_out[o] = z;
+    out = s1 * h2 + s2;
+  } else out = acc + (p1 ? e.alpha1 * s1 : 0.f) + (p2 ? e.alpha2 * s2 : 0.f);
+  g.C[o] = out;
 }
 
 // ---------------------------------------------------------------- the kernel
@@ -312,7 +290,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int raw_bytes = A_BYTES + b_bytes;
   const int stage_bytes = 2 * raw_bytes;
   const int STAGES = g.stages;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * stage_bytes);
+  float* epi_stage = reinterpret_cast<float*>(smem + (size_t)STAGES * stage_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * stage_bytes + EPI_SMEM_BYTES);
   uint64_t* full_bar = bars;                     // [STAGES] TMA landed
   uint64_t* conv_bar = bars + MAX_STAGES;        // [STAGES] hi/lo tiles ready
   uint64_t* empty_bar = bars + 2 * MAX_STAGES;   // [STAGES] MMAs that read the stage have completed
@@ -322,11 +301,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  int tcount = 0;   // debug trace cursor of this thread's role
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&conv_bar[s], 4);      // one arrival per converter warp
+      mbar_init(&conv_bar[s], NUM_CONV_THREADS / 32);   // one arrival per converter warp
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(&tmem_full[0], 1);
@@ -381,7 +361,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           else if (g.b_3d) tma_load_3d(sb, &tmap_b, 0, k0, tn * (g.bn / 32), &full_bar[stage]);            // box {32 n, 16 k, bn/32}
           else tma_load_2d(sb + blk * 2048, &tmap_b, tn * g.bn + blk * 32, k0, &full_bar[stage]);
         }
-        if (lane == 0) trace_ev(g.trace, 1, (unsigned)kb);
+        if (lane == 0) trace_ev(g.trace, 0, tcount, 1, (unsigned)kb);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -404,7 +384,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         mbar_wait(&conv_bar[stage], phase);
         tc_fence_after();
         if (lane == 0) {
-          trace_ev(g.trace, 4, (unsigned)kb);
+          trace_ev(g.trace, 1, tcount, 4, (unsigned)kb);
           const uint32_t a_hi = smem_u32(smem + (size_t)stage * stage_bytes);
           const uint32_t b_hi = a_hi + A_BYTES;
           const uint32_t a_lo = a_hi + raw_bytes;
@@ -422,7 +402,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
           tc_commit(&empty_bar[stage]);                       // frees the stage when these MMAs retire
           if (kb == kb1 - 1) tc_commit(&tmem_full[0]);        // accumulators complete
-          trace_ev(g.trace, 5, (unsigned)kb);
+          trace_ev(g.trace, 1, tcount, 5, (unsigned)kb);
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -432,7 +412,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
   } else if (warp >= 6) {
     // ======================= converters (warps 6..9: highest warp ids = highest issue priority) ===========
-    const int ct = threadIdx.x - 192;       // 0..127
+    const int ct = threadIdx.x - 192;       // 0..255
     int stage = 0;
     uint32_t phase = 0;
     const int nvec = raw_bytes / 16;
@@ -442,21 +422,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int64_t kb1 = imin<int64_t>(g.kblocks_total, kb0 + g.kblocks_per_split);
       for (int64_t kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase);
-        if (ct == 0) trace_ev(g.trace, 2, (unsigned)kb);
+        if (ct == 0) trace_ev(g.trace, 2, tcount, 2, (unsigned)kb);
         float4* raw = reinterpret_cast<float4*>(smem + (size_t)stage * stage_bytes);
         float4* lo = reinterpret_cast<float4*>(smem + (size_t)stage * stage_bytes + raw_bytes);
-        // all loads first (<= 12 float4 per thread at bn = 256), then split + store: one shared-memory
+        // all loads first (<= 6 float4 per thread at bn = 256), then split + store: one shared-memory
         // latency per k-block instead of one per element
-        constexpr int MAXV = (A_BYTES + MAX_BN * BK * 4) / 16 / 128;   // 12
+        constexpr int MAXV = (A_BYTES + MAX_BN * BK * 4) / 16 / NUM_CONV_THREADS;   // 6
         float4 xv[MAXV];
 #pragma unroll
         for (int j = 0; j < MAXV; ++j) {
-          const int i = ct + j * 128;
+          const int i = ct + j * NUM_CONV_THREADS;
           if (i < nvec) xv[j] = raw[i];
         }
 #pragma unroll
         for (int j = 0; j < MAXV; ++j) {
-          const int i = ct + j * 128;
+          const int i = ct + j * NUM_CONV_THREADS;
           if (i < nvec) {
             const float4 x = xv[j];
             float4 h, l;
@@ -472,63 +452,101 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             lo[i] = l;
           }
         }
-        if (ct == 0) trace_ev(g.trace, 8, (unsigned)kb);
+        if (ct == 0) trace_ev(g.trace, 2, tcount, 8, (unsigned)kb);
         // generic-proxy writes must be visible to the tensor core (async proxy) before the MMA reads them
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        if (ct == 0) trace_ev(g.trace, 9, (unsigned)kb);
+        if (ct == 0) trace_ev(g.trace, 2, tcount, 9, (unsigned)kb);
         __syncwarp();
         if (lane == 0) mbar_arrive(&conv_bar[stage]);
-        if (ct == 0) trace_ev(g.trace, 3, (unsigned)kb);
+        if (ct == 0) trace_ev(g.trace, 2, tcount, 3, (unsigned)kb);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else {
     // ======================= epilogue (warps 2..5) =======================
     const int quad = warp & 3;              // TMEM lane quadrant this warp may read
+    float* T = epi_stage + (warp - 2) * (32 * EPI_LD);     // this warp's 32 x 32 staging tile
+    const int rr = lane >> 3, c4 = lane & 7;               // coalesced domain: 4 rows x 8 float4 per instruction
+    const float* p1 = epi_stream1(g.epi);
+    const float* p2 = epi_stream2(g.epi);
     uint32_t acc_phase = 0;
     for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int split = (int)(tile / tiles_mn);
       const int64_t rem = tile - (int64_t)split * tiles_mn;
       const int tm = (int)(rem / g.tiles_n);
       const int tn = (int)(rem - (int64_t)tm * g.tiles_n);
-      const int64_t m = (int64_t)tm * BM + quad * 32 + lane;
-      const float* p1 = epi_stream1(g.epi);
-      const float* p2 = epi_stream2(g.epi);
+      const int64_t m_base = (int64_t)tm * BM + quad * 32;
       const int64_t nbase = (int64_t)tn * g.bn;
-      auto chunk_full = [&](int c) { return g.epi_vec && m < g.M && (nbase + c + 16) <= g.N; };
-      Aux16 a1, a2, b1, b2, bi;
-      // first chunk's operands are requested BEFORE waiting for the accumulator
-      aux_prefetch(p1, m * g.ldc + nbase, chunk_full(0), a1);
-      aux_prefetch(p2, m * g.ldc + nbase, chunk_full(0), a2);
+      // operand streams of chunk c for this lane's 8 (row, float4) slots; requested one chunk ahead
+      float4 a1[8], a2[8];
+      auto prefetch = [&](int c, float4 (&u1)[8], float4 (&u2)[8]) {
+        const int64_t n = nbase + c + c4 * 4;
+        const bool col_ok = g.epi_vec && (c + c4 * 4 < g.bn) && (n + 3 < g.N);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int64_t m = m_base + rr + 4 * i;
+          const bool ok = col_ok && m < g.M;
+          u1[i] = (ok && p1) ? __ldg(reinterpret_cast<const float4*>(p1 + m * g.ldc + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          u2[i] = (ok && p2) ? __ldg(reinterpret_cast<const float4*>(p2 + m * g.ldc + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
       mbar_wait_relaxed(&tmem_full[0], acc_phase);
       tc_fence_after();
-      if (warp == 2 && lane == 0) trace_ev(g.trace, 6, (unsigned)tile);
+      if (warp == 2 && lane == 0) trace_ev(g.trace, 3, tcount, 6, (unsigned)tile);
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16);
       const bool empty_k = ((int64_t)split * g.kblocks_per_split) >= g.kblocks_total;
-      for (int c = 0; c < g.bn; c += 16) {
-        if (c + 16 < g.bn) {
-          aux_prefetch(p1, m * g.ldc + nbase + c + 16, chunk_full(c + 16), b1);
-          aux_prefetch(p2, m * g.ldc + nbase + c + 16, chunk_full(c + 16), b2);
-        }
-        // bias chunk: same 64 bytes for every row -> read-only path, L1 resident after the first touch;
-        // issued before the TMEM loads so its latency overlaps them
-        aux_prefetch(g.epi.bias, nbase + c, chunk_full(c), bi);
+      for (int c = 0; c < g.bn; c += 32) {
+        // operand streams of this chunk are requested first; the TMEM loads + transpose below (~1K clocks)
+        // cover most of their latency without a second register buffer
+        prefetch(c, a1, a2);
+        const int64_t nq = nbase + c + c4 * 4;
+        const bool vec_ok = g.epi_vec && (c + c4 * 4 < g.bn) && (nq + 3 < g.N);
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (vec_ok && g.epi.bias) bv = __ldg(reinterpret_cast<const float4*>(g.epi.bias + nq));
+        if (warp == 2 && lane == 0) trace_ev(g.trace, 3, tcount, 10, (unsigned)c);
+        // TMEM -> registers (this lane = one row), main + cross-term accumulators, fp32 RN add
         uint32_t r[16], r2[16];
-        tc_ld16(t_row + (uint32_t)c, r);
-        tc_ld16(t_row + (uint32_t)(MAX_BN + c), r2);
-        tc_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          r[j] = empty_k ? 0u : __float_as_uint(__fadd_rn(__uint_as_float(r[j]), __uint_as_float(r2[j])));
-        const int64_t n0 = nbase + c;
-        if (m < g.M && n0 < g.N) epilogue_row16(g, m, n0, r, chunk_full(c), a1, a2, bi);
-        a1 = b1;
-        a2 = b2;
+        for (int half = 0; half < 2; ++half) {
+          if (c + 16 * half < g.bn) {
+            tc_ld16(t_row + (uint32_t)(c + 16 * half), r);
+            tc_ld16(t_row + (uint32_t)(MAX_BN + c + 16 * half), r2);
+            tc_wait_ld();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float4 v;
+              v.x = empty_k ? 0.f : __fadd_rn(__uint_as_float(r[4 * q + 0]), __uint_as_float(r2[4 * q + 0]));
+              v.y = empty_k ? 0.f : __fadd_rn(__uint_as_float(r[4 * q + 1]), __uint_as_float(r2[4 * q + 1]));
+              v.z = empty_k ? 0.f : __fadd_rn(__uint_as_float(r[4 * q + 2]), __uint_as_float(r2[4 * q + 2]));
+              v.w = empty_k ? 0.f : __fadd_rn(__uint_as_float(r[4 * q + 3]), __uint_as_float(r2[4 * q + 3]));
+              *reinterpret_cast<float4*>(T + lane * EPI_LD + 16 * half + 4 * q) = v;
+            }
+          }
+        }
+        __syncwarp();
+        if (warp == 2 && lane == 0) trace_ev(g.trace, 3, tcount, 11, (unsigned)c);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = rr + 4 * i;
+          const int64_t m = m_base + row;
+          if (m < g.M && (c + c4 * 4 < g.bn)) {
+            const float4 v = *reinterpret_cast<const float4*>(T + row * EPI_LD + c4 * 4);
+            if (vec_ok) {
+              epilogue_f4(g, m, nq, v, a1[i], a2[i], bv);
+            } else {
+              const float vv[4] = {v.x, v.y, v.z, v.w};
+              for (int j = 0; j < 4; ++j)
+                if (nq + j < g.N) epilogue_scalar(g, m, nq + j, vv[j]);
+            }
+          }
+        }
+        __syncwarp();                        // staging tile is rewritten by the next chunk
+        if (warp == 2 && lane == 0) trace_ev(g.trace, 3, tcount, 12, (unsigned)c);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[0]);
-      if (warp == 2 && lane == 0) trace_ev(g.trace, 7, (unsigned)tile);
+      if (warp == 2 && lane == 0) trace_ev(g.trace, 3, tcount, 7, (unsigned)tile);
       acc_phase ^= 1;
     }
   }
@@ -662,10 +680,10 @@ int gemm_tc(const float* A, int64_t lda, bool transA, const float* B, int64_t ld
     KRS_CUDA(cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, stream));
 
   const size_t stage_bytes = 2 * (size_t)(A_BYTES + g.bn * BK * 4);
-  const size_t budget = 227 * 1024 - 1024 - 512;                    // alignment slack + barriers
+  const size_t budget = 227 * 1024 - 1024 - 512 - EPI_SMEM_BYTES;   // alignment slack + barriers + epilogue staging
   g.stages = (int)imin<int64_t>(MAX_STAGES, (int64_t)(budget / stage_bytes));
   if (g.stages < 3) return KRS_EUNSUPPORTED;
-  const size_t smem = 1024 + g.stages * stage_bytes + 512;
+  const size_t smem = 1024 + g.stages * stage_bytes + EPI_SMEM_BYTES + 512;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {

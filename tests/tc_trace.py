@@ -13,12 +13,17 @@ def run():
     check(lib.krs_cross_fwd(ptr(x0), ptr(x0), None, ptr(V), ptr(b), 0.0, 0, ptr(y), ptr(h2), None, None, B, D, 0, stream()))
 for _ in range(2): run()
 torch.cuda.synchronize()
-tr = torch.zeros(16001, dtype=torch.int64, device="cuda")
+tr = torch.zeros(16001 + 16, dtype=torch.int64, device="cuda")
 lib.krs_gemm_tc_set_trace(tr.data_ptr())
 run(); torch.cuda.synchronize()
 lib.krs_gemm_tc_set_trace(None)
 t = tr.cpu().numpy()
-n = int(t[0]); ev = [(int(t[1+2*i]) >> 32, int(t[1+2*i]) & 0xffffffff, int(t[2+2*i])) for i in range(min(n, 8000))]
+ev = []
+for role in range(4):
+    for i in range(2000):
+        a, c = int(t[1 + role * 4000 + 2 * i]), int(t[2 + role * 4000 + 2 * i])
+        if c: ev.append((a >> 32, a & 0xffffffff, c))
+n = len(ev)
 ev.sort(key=lambda e: e[2]); t0 = ev[0][2]
 names = {8: "conv stores issued", 9: "conv fence done", 1: "TMA issued", 2: "conv saw full", 3: "conv done", 4: "mma saw conv", 5: "mma committed", 6: "epi start", 7: "epi done"}
 print("entries", n)
@@ -39,3 +44,10 @@ for tile in (0, 1, 2):
           f"TMA issue->full seen median {np.median(np.array(s2)-np.array(s1)):.0f}; conv time median {np.median(np.array(s3)-np.array(s2)):.0f}; "
           f"conv done->mma saw {np.median(np.array(s4)-np.array(s3)):.0f}; mma issue {np.median(np.array(s5)-np.array(s4)):.0f}")
     print("   first 8 kb: TMA", [c - s1[0] for c in s1[:8]], " full", [c - s1[0] for c in s2[:8]], " convdone", [c - s1[0] for c in s3[:8]], " commit", [c - s1[0] for c in s5[:8]])
+
+# epilogue chunk breakdown (first tile)
+e10 = [c for tag, i, c in ev if tag == 10][:14]; e11 = [c for tag, i, c in ev if tag == 11][:14]; e12 = [c for tag, i, c in ev if tag == 12][:14]
+if len(e12) == 14:
+    print("epilogue chunks (tile 0): begin->tmem loaded", [b - a for a, b in zip(e10, e11)])
+    print("                          loaded->chunk done ", [b - a for a, b in zip(e11, e12)])
+    print("                          chunk period       ", list(np.diff(np.array(e10))))
