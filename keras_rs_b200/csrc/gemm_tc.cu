@@ -17,7 +17,8 @@
 //   warps 6-13  converters: shared -> registers -> shared, write hi (in place) and lo tiles (highest
 //               warp ids: the scheduler arbitrates highest-warp-id first and they are the critical stage)
 // Shared memory ring: 4 stages x (A_raw | B_raw | A_lo | B_lo), BK = 16 floats per stage.
-// TMEM: 512 columns = TWO accumulators x 256 columns (128 lanes = the 128 rows of the tile): the hi·hi
+// TMEM: 512 columns = 2 stages x TWO accumulators x 128 columns (128 lanes = the 128 rows of the tile), so the
+// epilogue of tile i overlaps the mainloop of tile i+1.  Within a stage the hi·hi
 // products and the small cross terms (lo·hi + hi·lo) accumulate separately and are added in fp32
 // registers by the epilogue.  Reason (measured, tests/test_gpu_tc.py): the tensor core's fp32
 // accumulate truncates, so the error grows with the number of accumulations into one TMEM tile
@@ -46,7 +47,7 @@ namespace {
 constexpr int BM = 128;          // rows per tile == TMEM lanes
 constexpr int BK = 16;           // fp32 elements per k-block (64 B)
 constexpr int MAX_STAGES = 12;    // ring depth is chosen per launch from the shared-memory budget
-constexpr int MAX_BN = 256;
+constexpr int MAX_BN = 128;       // 2 accumulator stages x (main + cross-term) x 128 columns = 512 TMEM columns
 constexpr int NUM_THREADS = 448;          // TMA, MMA, 4 epilogue warps, 8 converter warps
 constexpr int NUM_CONV_THREADS = 256;
 constexpr int EPI_LD = 36;                // staging row pitch in floats (32 + 4: conflict-free 16-byte accesses)
@@ -309,8 +310,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_init(&conv_bar[s], NUM_CONV_THREADS / 32);   // one arrival per converter warp
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(&tmem_full[0], 1);
-    mbar_init(&tmem_empty[0], 4);      // one arrival per epilogue warp
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 4);    // one arrival per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -371,15 +374,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                            ((uint32_t)g.b_mn_major << 16) | ((uint32_t)(g.bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
     int stage = 0;
     uint32_t phase = 0;
+    int acc = 0;
     uint32_t acc_phase = 0;
-    const uint32_t d_main = tmem_base;
-    const uint32_t d_small = tmem_base + (uint32_t)MAX_BN;
     for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int split = (int)(tile / tiles_mn);
       const int64_t kb0 = (int64_t)split * g.kblocks_per_split;
       const int64_t kb1 = imin<int64_t>(g.kblocks_total, kb0 + g.kblocks_per_split);
-      mbar_wait_relaxed(&tmem_empty[0], acc_phase ^ 1);
+      mbar_wait_relaxed(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
+      const uint32_t d_main = tmem_base + (uint32_t)(acc * 2 * MAX_BN);
+      const uint32_t d_small = d_main + (uint32_t)MAX_BN;
       for (int64_t kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&conv_bar[stage], phase);
         tc_fence_after();
@@ -401,14 +405,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             tc_mma_tf32(d_main, dah, dbh, idesc, first);     // main term
           }
           tc_commit(&empty_bar[stage]);                       // frees the stage when these MMAs retire
-          if (kb == kb1 - 1) tc_commit(&tmem_full[0]);        // accumulators complete
+          if (kb == kb1 - 1) tc_commit(&tmem_full[acc]);      // accumulators complete
           trace_ev(g.trace, 1, tcount, 5, (unsigned)kb);
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      if (kb1 <= kb0 && lane == 0) tc_commit(&tmem_full[0]);  // empty K range: nothing accumulated
-      acc_phase ^= 1;
+      if (kb1 <= kb0 && lane == 0) tc_commit(&tmem_full[acc]);  // empty K range: nothing accumulated
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 6) {
     // ======================= converters (warps 6..9: highest warp ids = highest issue priority) ===========
@@ -469,6 +473,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int rr = lane >> 3, c4 = lane & 7;               // coalesced domain: 4 rows x 8 float4 per instruction
     const float* p1 = epi_stream1(g.epi);
     const float* p2 = epi_stream2(g.epi);
+    // L2 prefetch of the epilogue operand tiles (x0 / x, add1 / add2) of a FUTURE tile: issued one tile ahead so the
+    // epilogue's loads hit L2 instead of paying DRAM latency with only 4 warps' worth of requests in flight
+    auto prefetch_tile_l2 = [&](int64_t t) {
+      if (t >= total_tiles || (p1 == nullptr && p2 == nullptr)) return;
+      const int sp = (int)(t / tiles_mn);
+      const int64_t rm = t - (int64_t)sp * tiles_mn;
+      const int ptm = (int)(rm / g.tiles_n);
+      const int ptn = (int)(rm - (int64_t)ptm * g.tiles_n);
+      const int64_t m = (int64_t)ptm * BM + quad * 32 + lane;
+      if (m >= g.M) return;
+      const int64_t n0 = (int64_t)ptn * g.bn;
+      const int64_t ncols = imin<int64_t>(g.bn, g.N - n0);
+      for (int64_t c = 0; c < ncols; c += 32) {
+        if (p1) asm volatile("prefetch.global.L2 [%0];" ::"l"(p1 + m * g.ldc + n0 + c));
+        if (p2) asm volatile("prefetch.global.L2 [%0];" ::"l"(p2 + m * g.ldc + n0 + c));
+      }
+    };
+    prefetch_tile_l2(blockIdx.x);
+    int acc = 0;
     uint32_t acc_phase = 0;
     for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int split = (int)(tile / tiles_mn);
@@ -477,6 +500,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int tn = (int)(rem - (int64_t)tm * g.tiles_n);
       const int64_t m_base = (int64_t)tm * BM + quad * 32;
       const int64_t nbase = (int64_t)tn * g.bn;
+      prefetch_tile_l2(tile + gridDim.x);
       // operand streams of chunk c for this lane's 8 (row, float4) slots; requested one chunk ahead
       float4 a1[8], a2[8];
       auto prefetch = [&](int c, float4 (&u1)[8], float4 (&u2)[8]) {
@@ -490,10 +514,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           u2[i] = (ok && p2) ? __ldg(reinterpret_cast<const float4*>(p2 + m * g.ldc + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       };
-      mbar_wait_relaxed(&tmem_full[0], acc_phase);
+      mbar_wait_relaxed(&tmem_full[acc], acc_phase);
       tc_fence_after();
       if (warp == 2 && lane == 0) trace_ev(g.trace, 3, tcount, 6, (unsigned)tile);
-      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16);
+      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * 2 * MAX_BN);
       const bool empty_k = ((int64_t)split * g.kblocks_per_split) >= g.kblocks_total;
       for (int c = 0; c < g.bn; c += 32) {
         // operand streams of this chunk are requested first; the TMEM loads + transpose below (~1K clocks)
@@ -545,9 +569,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[0]);
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (warp == 2 && lane == 0) trace_ev(g.trace, 3, tcount, 7, (unsigned)tile);
-      acc_phase ^= 1;
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 

@@ -46,8 +46,8 @@ for tile in (0, 1, 2):
     print("   first 8 kb: TMA", [c - s1[0] for c in s1[:8]], " full", [c - s1[0] for c in s2[:8]], " convdone", [c - s1[0] for c in s3[:8]], " commit", [c - s1[0] for c in s5[:8]])
 
 # epilogue chunk breakdown (first tile)
-e10 = [c for tag, i, c in ev if tag == 10][:14]; e11 = [c for tag, i, c in ev if tag == 11][:14]; e12 = [c for tag, i, c in ev if tag == 12][:14]
-if len(e12) == 14:
+e10 = [c for tag, i, c in ev if tag == 10][:8]; e11 = [c for tag, i, c in ev if tag == 11][:8]; e12 = [c for tag, i, c in ev if tag == 12][:8]
+if len(e12) >= 4:
     print("epilogue chunks (tile 0): begin->tmem loaded", [b - a for a, b in zip(e10, e11)])
     print("                          loaded->chunk done ", [b - a for a, b in zip(e11, e12)])
     print("                          chunk period       ", list(np.diff(np.array(e10))))
