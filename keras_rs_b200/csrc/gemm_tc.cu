@@ -48,7 +48,8 @@ constexpr int BM = 128;          // rows per tile == TMEM lanes
 constexpr int BK = 16;           // fp32 elements per k-block (64 B)
 constexpr int MAX_STAGES = 12;    // ring depth is chosen per launch from the shared-memory budget
 constexpr int MAX_BN = 128;       // 2 accumulator stages x (main + cross-term) x 128 columns = 512 TMEM columns
-constexpr int NUM_THREADS = 448;          // TMA, MMA, 4 epilogue warps, 8 converter warps
+constexpr int NUM_THREADS = 512;          // WG0: 4 epilogue warps | WG1-2: 8 converter warps | WG3: TMA, MMA, 2 idle
+constexpr int W_TMA = 12, W_MMA = 13;
 constexpr int NUM_CONV_THREADS = 256;
 constexpr int EPI_LD = 36;                // staging row pitch in floats (32 + 4: conflict-free 16-byte accesses)
 constexpr int EPI_SMEM_BYTES = 4 * 32 * EPI_LD * 4;   // one 32x32 staging tile per epilogue warp
@@ -316,7 +317,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {
+  if (warp == W_MMA) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -324,11 +325,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-
   const int64_t tiles_mn = (int64_t)g.tiles_m * g.tiles_n;
   const int64_t total_tiles = tiles_mn * g.splits;
 
-  if (warp == 0) {
+  // register budget per role (warpgroup granular; 512 threads start at 128 registers each): the epilogue needs
+  // room for a chunk of operand prefetches, converters / TMA / MMA need little.  Each role's branch begins with
+  // its own setmaxnreg so that ptxas allocates that branch against the adjusted budget.
+  if (warp >= 12) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(56));
+  if (warp == W_TMA) {
     // ======================= TMA producer =======================
     // every lane waits for the free stage; lane 0 arms the transaction count, then the boxes of the stage
     // (1 per K-major operand, bn/32 or 4 per MN-major operand) are issued by different lanes in parallel
@@ -368,7 +372,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == W_MMA) {
     // ======================= MMA issuer =======================
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)g.a_mn_major << 15) |
                            ((uint32_t)g.b_mn_major << 16) | ((uint32_t)(g.bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
@@ -376,6 +380,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
+    const uint32_t s0 = smem_u32(smem);
+    const uint64_t dA_hi = g.a_mn_major ? desc_mnmajor(s0, 0, g) : desc_kmajor(s0, 0);
+    const uint64_t dA_lo = g.a_mn_major ? desc_mnmajor(s0 + raw_bytes, 0, g) : desc_kmajor(s0 + raw_bytes, 0);
+    const uint64_t dB_hi = g.b_mn_major ? desc_mnmajor(s0 + A_BYTES, 0, g) : desc_kmajor(s0 + A_BYTES, 0);
+    const uint64_t dB_lo = g.b_mn_major ? desc_mnmajor(s0 + A_BYTES + raw_bytes, 0, g) : desc_kmajor(s0 + A_BYTES + raw_bytes, 0);
+    const uint32_t a_kstep16 = (uint32_t)(g.a_mn_major ? g.mn_kstep : 32) >> 4;
+    const uint32_t b_kstep16 = (uint32_t)(g.b_mn_major ? g.mn_kstep : 32) >> 4;
     for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int split = (int)(tile / tiles_mn);
       const int64_t kb0 = (int64_t)split * g.kblocks_per_split;
@@ -389,16 +400,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         tc_fence_after();
         if (lane == 0) {
           trace_ev(g.trace, 1, tcount, 4, (unsigned)kb);
-          const uint32_t a_hi = smem_u32(smem + (size_t)stage * stage_bytes);
-          const uint32_t b_hi = a_hi + A_BYTES;
-          const uint32_t a_lo = a_hi + raw_bytes;
-          const uint32_t b_lo = b_hi + raw_bytes;
+          // descriptors = per-launch base (stage 0, k-step 0) + (stage offset + k-step offset) >> 4 in the
+          // 14-bit start-address field: one 32-bit add each instead of rebuilding the bit fields
+          const uint32_t so = (uint32_t)(stage * stage_bytes) >> 4;
 #pragma unroll
           for (int ks = 0; ks < BK / 8; ++ks) {
-            const uint64_t dah = g.a_mn_major ? desc_mnmajor(a_hi, ks, g) : desc_kmajor(a_hi, ks);
-            const uint64_t dal = g.a_mn_major ? desc_mnmajor(a_lo, ks, g) : desc_kmajor(a_lo, ks);
-            const uint64_t dbh = g.b_mn_major ? desc_mnmajor(b_hi, ks, g) : desc_kmajor(b_hi, ks);
-            const uint64_t dbl = g.b_mn_major ? desc_mnmajor(b_lo, ks, g) : desc_kmajor(b_lo, ks);
+            const uint64_t dah = dA_hi + so + (ks ? a_kstep16 : 0u);
+            const uint64_t dal = dA_lo + so + (ks ? a_kstep16 : 0u);
+            const uint64_t dbh = dB_hi + so + (ks ? b_kstep16 : 0u);
+            const uint64_t dbl = dB_lo + so + (ks ? b_kstep16 : 0u);
             const uint32_t first = (kb == kb0 && ks == 0) ? 0u : 1u;
             tc_mma_tf32(d_small, dal, dbh, idesc, first);    // cross terms: their own accumulator
             tc_mma_tf32(d_small, dah, dbl, idesc, 1u);
@@ -414,9 +424,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       if (kb1 <= kb0 && lane == 0) tc_commit(&tmem_full[acc]);  // empty K range: nothing accumulated
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-  } else if (warp >= 6) {
-    // ======================= converters (warps 6..9: highest warp ids = highest issue priority) ===========
-    const int ct = threadIdx.x - 192;       // 0..255
+  } else if (warp >= 4 && warp < 12) {
+    // ======================= converters (warps 4..11) =======================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(80));
+    const int ct = threadIdx.x - 128;       // 0..255
     int stage = 0;
     uint32_t phase = 0;
     const int nvec = raw_bytes / 16;
@@ -466,10 +477,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else {
-    // ======================= epilogue (warps 2..5) =======================
+  } else if (warp < 4) {
+    // ======================= epilogue (warps 0..3) =======================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(224));
     const int quad = warp & 3;              // TMEM lane quadrant this warp may read
-    float* T = epi_stage + (warp - 2) * (32 * EPI_LD);     // this warp's 32 x 32 staging tile
+    float* T = epi_stage + warp * (32 * EPI_LD);           // this warp's 32 x 32 staging tile
     const int rr = lane >> 3, c4 = lane & 7;               // coalesced domain: 4 rows x 8 float4 per instruction
     const float* p1 = epi_stream1(g.epi);
     const float* p2 = epi_stream2(g.epi);
@@ -516,7 +528,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       };
       mbar_wait_relaxed(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      if (warp == 2 && lane == 0) trace_ev(g.trace, 3, tcount, 6, (unsigned)tile);
+      if (warp == 0 && lane == 0) trace_ev(g.trace, 3, tcount, 6, (unsigned)tile);
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * 2 * MAX_BN);
       const bool empty_k = ((int64_t)split * g.kblocks_per_split) >= g.kblocks_total;
       for (int c = 0; c < g.bn; c += 32) {
@@ -527,7 +539,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const bool vec_ok = g.epi_vec && (c + c4 * 4 < g.bn) && (nq + 3 < g.N);
         float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (vec_ok && g.epi.bias) bv = __ldg(reinterpret_cast<const float4*>(g.epi.bias + nq));
-        if (warp == 2 && lane == 0) trace_ev(g.trace, 3, tcount, 10, (unsigned)c);
+        if (warp == 0 && lane == 0) trace_ev(g.trace, 3, tcount, 10, (unsigned)c);
         // TMEM -> registers (this lane = one row), main + cross-term accumulators, fp32 RN add
         uint32_t r[16], r2[16];
 #pragma unroll
@@ -548,7 +560,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
         }
         __syncwarp();
-        if (warp == 2 && lane == 0) trace_ev(g.trace, 3, tcount, 11, (unsigned)c);
+        if (warp == 0 && lane == 0) trace_ev(g.trace, 3, tcount, 11, (unsigned)c);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int row = rr + 4 * i;
@@ -565,19 +577,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
         }
         __syncwarp();                        // staging tile is rewritten by the next chunk
-        if (warp == 2 && lane == 0) trace_ev(g.trace, 3, tcount, 12, (unsigned)c);
+        if (warp == 0 && lane == 0) trace_ev(g.trace, 3, tcount, 12, (unsigned)c);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-      if (warp == 2 && lane == 0) trace_ev(g.trace, 3, tcount, 7, (unsigned)tile);
+      if (warp == 0 && lane == 0) trace_ev(g.trace, 3, tcount, 7, (unsigned)tile);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == W_MMA) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
   }
