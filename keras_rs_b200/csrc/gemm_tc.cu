@@ -101,6 +101,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// Critical-path wait: try_wait with a suspend-time hint compiles to TRYWAIT + NANOSLEEP.SYNCS — the warp is
+// parked by the hardware and woken by the barrier's phase change, so a waiting role does not burn issue slots
+// that lower-priority warps (the epilogue) need.  A tight try_wait spin starved them (tests/tc_trace.py).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t ok = 0;
@@ -109,7 +112,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x400;\n"
         "selp.u32 %0, 1, 0, p;\n"
         "}\n"
         : "=r"(ok)

@@ -9,8 +9,19 @@ B, D = 65536, 832
 g = torch.Generator(device="cuda").manual_seed(0)
 x0 = torch.randn((B, D), device="cuda", generator=g); V = torch.randn((D, D), device="cuda", generator=g) * 0.03
 b = torch.zeros(D, device="cuda"); y = torch.empty_like(x0); h2 = torch.empty_like(x0)
+MODE = os.environ.get("MODE", "cross")
+x1 = torch.randn((B, D), device="cuda", generator=g)
 def run():
-    check(lib.krs_cross_fwd(ptr(x0), ptr(x0), None, ptr(V), ptr(b), 0.0, 0, ptr(y), ptr(h2), None, None, B, D, 0, stream()))
+    if MODE == "cross":
+        check(lib.krs_cross_fwd(ptr(x0), ptr(x0), None, ptr(V), ptr(b), 0.0, 0, ptr(y), ptr(h2), None, None, B, D, 0, stream()))
+    elif MODE == "cross_noh2":
+        check(lib.krs_cross_fwd(ptr(x0), ptr(x0), None, ptr(V), ptr(b), 0.0, 0, ptr(y), None, None, None, B, D, 0, stream()))
+    elif MODE == "cross_x1":   # x != x0: the epilogue's second stream is NOT what TMA just read
+        check(lib.krs_cross_fwd(ptr(x0), ptr(x1), None, ptr(V), ptr(b), 0.0, 0, ptr(y), ptr(h2), None, None, B, D, 0, stream()))
+    elif MODE == "dense":
+        check(lib.krs_dense_fwd(ptr(x0), ptr(V), ptr(b), 0, ptr(y), B, D, D, stream()))
+    else:
+        K.ops.sgemm(x0, V, out=y)
 for _ in range(2): run()
 torch.cuda.synchronize()
 tr = torch.zeros(16001 + 16, dtype=torch.int64, device="cuda")
@@ -26,7 +37,7 @@ for role in range(4):
 n = len(ev)
 ev.sort(key=lambda e: e[2]); t0 = ev[0][2]
 names = {8: "conv stores issued", 9: "conv fence done", 1: "TMA issued", 2: "conv saw full", 3: "conv done", 4: "mma saw conv", 5: "mma committed", 6: "epi start", 7: "epi done"}
-print("entries", n)
+print("MODE", MODE, "entries", n)
 by = {k: [(i, c - t0) for tag, i, c in ev if tag == k] for k in names}
 for k in (6, 7):
     print(names[k], by[k][:6])
