@@ -276,9 +276,16 @@ __global__ void __launch_bounds__(256) gather_generic_kernel(const __grid_consta
 }
 
 // ------------------------------------------------------------------ backward
-// Fast path: 1-hot, no weights (weight 1), any E; warp = 32 consecutive samples of one feature.
-template <typename IdT>
+// Fast path: 1-hot, weight 1; warp = 32 consecutive samples of one feature.  Duplicate ids inside the warp
+// are found with __match_any_sync; each distinct id ("leader") gets ONE accumulated row.
+//   VEC variant (E = 4*LPR, LPR a power of two <= 32): LPR lanes own a row, RPW = 32/LPR leader rows are
+//   processed per step, each lane sums its float4 over the duplicate samples and issues ONE 16-byte
+//   RED.E.ADD.F32x4 — 4x fewer (and 4x wider) reductions than the scalar form, which matters most for
+//   row-sharded tables where the reduction crosses NVLink to the owning GPU.
+template <typename IdT, int LPR>
 __global__ void __launch_bounds__(256) scatter_fast_kernel(const __grid_constant__ GatherParams p) {
+  constexpr bool VEC = LPR > 0;
+  constexpr int RPW = VEC ? 32 / (LPR > 0 ? LPR : 1) : 1;
   const int lane = threadIdx.x & 31;
   const int64_t nblk = (p.B + 31) >> 5;                 // sample blocks
   const int64_t items = nblk * p.F;                     // item = (sample block, feature), feature fastest
@@ -295,11 +302,12 @@ __global__ void __launch_bounds__(256) scatter_fast_kernel(const __grid_constant
     if (valid) id = clamp_id(load_id<IdT>(ft.ids, b * ft.ids_stride), ft.vocab);
     const unsigned peers = __match_any_sync(0xffffffffu, id);
     const bool leader = valid && ((__ffs(peers) - 1) == lane);
+    const int S = ft.num_shards;
     if (leader) {
-      if (ft.num_shards > 1) {
+      if (S > 1) {
         if (ft.shard_touched) {
-          const int64_t lr = id / ft.num_shards;
-          atomicOr(ft.shard_touched[(int)(id % ft.num_shards)] + (lr >> 5), 1u << (lr & 31));
+          const int64_t lr = id / S;
+          atomicOr(ft.shard_touched[(int)(id % S)] + (lr >> 5), 1u << (lr & 31));
         }
       } else if (ft.touched) {
         atomicOr(ft.touched + (id >> 5), 1u << (id & 31));
@@ -307,20 +315,40 @@ __global__ void __launch_bounds__(256) scatter_fast_kernel(const __grid_constant
     }
     const unsigned leaders = __ballot_sync(0xffffffffu, leader);
     const int E = ft.dim;
-    for (unsigned m = leaders; m; m &= m - 1) {
-      const int r = __ffs(m) - 1;
-      const int64_t rid = __shfl_sync(0xffffffffu, id, r);
-      const unsigned rp = __shfl_sync(0xffffffffu, peers, r);
-      float* drow;
-      if (ft.num_shards > 1) drow = ft.shard_grads[(int)(rid % ft.num_shards)] + (rid / ft.num_shards) * (int64_t)E;
-      else drow = ft.grad + rid * (int64_t)E;
-      for (int c = lane; c < E; c += 32) {
-        float acc = 0.f;
-        for (unsigned q = rp; q; q &= q - 1) {
-          const int j = __ffs(q) - 1;
-          acc += gout[(b0 + j) * p.out_ld + ft.out_offset + c];
+    if (VEC) {
+      const int sub = lane % (LPR > 0 ? LPR : 1), rsub = lane / (LPR > 0 ? LPR : 1);
+      const int nlead = __popc(leaders);
+      for (int base = 0; base < nlead; base += RPW) {
+        const int nth = base + rsub;                     // this lane group's leader (nth set bit)
+        const bool act = nth < nlead;
+        const int r = act ? (int)__fns(leaders, 0, nth + 1) : 0;
+        const int64_t rid = __shfl_sync(0xffffffffu, id, r);
+        const unsigned rp = __shfl_sync(0xffffffffu, peers, r);
+        if (act) {
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (unsigned q = rp; q; q &= q - 1) {
+            const int j = __ffs(q) - 1;
+            const float4 v = ldg_nc_f4(gout + (b0 + j) * p.out_ld + ft.out_offset + sub * 4);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+          }
+          float* drow = (S > 1) ? ft.shard_grads[(int)(rid % S)] + (rid / S) * (int64_t)E : ft.grad + rid * (int64_t)E;
+          atomicAdd(reinterpret_cast<float4*>(drow + sub * 4), acc);
         }
-        atomicAdd(drow + c, acc);
+      }
+    } else {
+      for (unsigned m = leaders; m; m &= m - 1) {
+        const int r = __ffs(m) - 1;
+        const int64_t rid = __shfl_sync(0xffffffffu, id, r);
+        const unsigned rp = __shfl_sync(0xffffffffu, peers, r);
+        float* drow = (S > 1) ? ft.shard_grads[(int)(rid % S)] + (rid / S) * (int64_t)E : ft.grad + rid * (int64_t)E;
+        for (int c = lane; c < E; c += 32) {
+          float acc = 0.f;
+          for (unsigned q = rp; q; q &= q - 1) {
+            const int j = __ffs(q) - 1;
+            acc += gout[(b0 + j) * p.out_ld + ft.out_offset + c];
+          }
+          atomicAdd(drow + c, acc);
+        }
       }
     }
   }
@@ -530,8 +558,26 @@ extern "C" int krs_gather_bwd(const krs_feature_t* features, int F, int64_t B, c
   if (fast) {
     const int64_t items = ceil_div<int64_t>(B, 32) * F;
     const unsigned grid = (unsigned)krs::imax<int64_t>(1, krs::imin<int64_t>(ceil_div<int64_t>(items, 8), 0x7fffffff));
-    if (is64) scatter_fast_kernel<int64_t><<<grid, 256, 0, s>>>(p);
-    else scatter_fast_kernel<int32_t><<<grid, 256, 0, s>>>(p);
+    // vector variant: every feature has the same E = 4*LPR (LPR in {1,2,4,8,16,32}) and 16-byte aligned rows
+    int E0 = p.f[0].dim;
+    bool vec = (E0 % 4 == 0) && ((E0 / 4) & (E0 / 4 - 1)) == 0 && E0 <= 128 && aligned16(gout) && (gout_ld % 4 == 0);
+    for (int i = 0; i < F && vec; ++i) {
+      const krs_feature_t& f = p.f[i];
+      if (f.dim != E0 || (f.out_offset % 4) != 0) vec = false;
+      if (f.num_shards <= 1 && !aligned16(f.grad)) vec = false;
+    }
+#define KRS_SCAT(L)                                                                                   \
+  case L:                                                                                             \
+    if (is64) scatter_fast_kernel<int64_t, L><<<grid, 256, 0, s>>>(p);                                \
+    else scatter_fast_kernel<int32_t, L><<<grid, 256, 0, s>>>(p);                                     \
+    break;
+    switch (vec ? E0 / 4 : 0) {
+      KRS_SCAT(1) KRS_SCAT(2) KRS_SCAT(4) KRS_SCAT(8) KRS_SCAT(16) KRS_SCAT(32)
+      default:
+        if (is64) scatter_fast_kernel<int64_t, 0><<<grid, 256, 0, s>>>(p);
+        else scatter_fast_kernel<int32_t, 0><<<grid, 256, 0, s>>>(p);
+    }
+#undef KRS_SCAT
   } else {
     const int64_t items = B * F;
     const unsigned grid = (unsigned)krs::imax<int64_t>(1, krs::imin<int64_t>(ceil_div<int64_t>(items, 8), (int64_t)sm_count() * 32));
