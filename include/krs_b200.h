@@ -87,8 +87,17 @@ typedef struct krs_feature {
   float* const* shard_grads;
   uint32_t* const* shard_touched; /* bwd only, nullable: per-shard bitmaps indexed by LOCAL row     */
   int32_t num_shards;
-  int32_t _pad;
+  int32_t shard_mode;     /* low byte: how a sharded feature is addressed; second byte: this rank's shard id  */
+                          /*  0 KRS_SHARD_DIRECT  : row = shard_tables[id%S] + (id/S)*E  (peer-mapped tables)  */
+                          /*  1 KRS_SHARD_OWNER   : only ids with id%S == me; row = table + (id/S)*E (fwd) or */
+                          /*                        grad + (id/S)*E (bwd); other positions are skipped        */
+                          /*  2 KRS_SHARD_POSITION: row = shard_tables[id%S] + pos*E (fwd pull) or            */
+                          /*                        shard_grads[id%S] + pos*E (bwd push, plain stores),       */
+                          /*                        pos = b*F + f: monotonic remote addresses                 */
 } krs_feature_t;
+#define KRS_SHARD_DIRECT 0
+#define KRS_SHARD_OWNER 1
+#define KRS_SHARD_POSITION 2
 
 /* features: HOST array of F descriptors (copied into kernel parameters; F <= 96 per call).
  * out: (B, out_ld) fp32. */

@@ -37,7 +37,7 @@ class KrsFeature(C.Structure):
         ("combiner", C.c_int32), ("ids_i64", C.c_int32), ("reduce", C.c_int32),
         ("shard_tables", C.c_void_p), ("shard_grads", C.c_void_p), ("shard_touched", C.c_void_p),
         ("num_shards", C.c_int32),
-        ("_pad", C.c_int32),
+        ("shard_mode", C.c_int32),
     ]
 
 

@@ -66,6 +66,7 @@ struct FeatLite {
   const float* const* shards;
   int nshards;
   int shard_shift;   // log2(nshards) when it is a power of two, else -1
+  int mode, me;      // KRS_SHARD_* addressing mode and this rank's shard id
 };
 
 template <int LPR, typename IdT, bool SHARDED>
@@ -84,6 +85,8 @@ __global__ void __launch_bounds__(256) gather_fast_kernel(const __grid_constant_
     t.shards = p.f[i].shard_tables;
     t.nshards = p.f[i].num_shards;
     t.shard_shift = (t.nshards > 0 && (t.nshards & (t.nshards - 1)) == 0) ? (31 - __clz(t.nshards)) : -1;
+    t.mode = p.f[i].shard_mode & 0xff;
+    t.me = (p.f[i].shard_mode >> 8) & 0xff;
     sf[i] = t;
   }
   __syncthreads();
@@ -107,7 +110,9 @@ __global__ void __launch_bounds__(256) gather_fast_kernel(const __grid_constant_
         const int sh = ft.shard_shift;
         const int owner = sh >= 0 ? (int)(id & (ft.nshards - 1)) : (int)(id % ft.nshards);
         const long long local = sh >= 0 ? (id >> sh) : (id / ft.nshards);
-        src = ft.shards[owner] + local * E;          // peer-mapped shard: the row crosses NVLink here
+        if (ft.mode == KRS_SHARD_OWNER) src = (owner == ft.me) ? ft.table + local * E : nullptr;   // rows I own, local table
+        else if (ft.mode == KRS_SHARD_POSITION) src = ft.shards[owner] + (r0 + lane) * E;          // monotonic pull from the owner's staging
+        else src = ft.shards[owner] + local * E;      // direct peer-mapped table (random remote rows: slow over NVLink)
       } else {
         src = ft.table + id * E;
       }
@@ -297,12 +302,19 @@ __global__ void __launch_bounds__(256) scatter_fast_kernel(const __grid_constant
     const krs_feature_t& ft = p.f[f];
     const int64_t b0 = blk << 5;
     const int64_t b = b0 + lane;
-    const bool valid = b < p.B;
+    bool valid = b < p.B;
     int64_t id = -1 - lane;                              // unique negative sentinel for tail lanes
     if (valid) id = clamp_id(load_id<IdT>(ft.ids, b * ft.ids_stride), ft.vocab);
+    int S = ft.num_shards;
+    if (S > 1 && (ft.shard_mode & 0xff) == KRS_SHARD_OWNER) {
+      // owner-side scatter of a peer's staged gradient rows: keep only the ids this rank owns and address
+      // the LOCAL arena by local row (all random traffic stays on this GPU)
+      if (valid && (int)(id % S) != ((ft.shard_mode >> 8) & 0xff)) { valid = false; id = -1 - lane; }
+      else if (valid) id = id / S;
+      S = 1;
+    }
     const unsigned peers = __match_any_sync(0xffffffffu, id);
     const bool leader = valid && ((__ffs(peers) - 1) == lane);
-    const int S = ft.num_shards;
     if (leader) {
       if (S > 1) {
         if (ft.shard_touched) {
@@ -350,6 +362,42 @@ __global__ void __launch_bounds__(256) scatter_fast_kernel(const __grid_constant
           atomicAdd(drow + c, acc);
         }
       }
+    }
+  }
+}
+
+
+// ------------------------------------------------------------------ backward, positional push (KRS_SHARD_POSITION)
+// Row-sharded tables: every gradient row (b,f) is copied with plain 16-byte stores into the OWNER's staging
+// buffer at position b*F+f (shard_grads[id % S] + pos*E).  Remote addresses increase monotonically, so the NVLink
+// stream is sequential; the owner later scatter-adds its staged rows locally (KRS_SHARD_OWNER).
+template <int LPR, typename IdT>
+__global__ void __launch_bounds__(256) push_rows_kernel(const __grid_constant__ GatherParams p) {
+  constexpr int RPW = 32 / LPR;
+  constexpr int E = LPR * 4;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane % LPR, rsub = lane / LPR;
+  const unsigned F = (unsigned)p.F;
+  const long long R = p.B * (long long)p.F;
+  const float* __restrict__ gout = p.out;
+  const long long r0 = ((long long)blockIdx.x * 8 + warp) * 32;
+  if (r0 >= R) return;
+  long long b = r0 / F;
+  unsigned f = (unsigned)(r0 - b * F) + lane;
+  while (f >= F) { f -= F; ++b; }
+  float* dst = nullptr;
+  if (r0 + lane < R) {
+    const krs_feature_t& ft = p.f[f];
+    const long long id = clamp_id(load_id<IdT>(ft.ids, b * ft.ids_stride), ft.vocab);
+    dst = ft.shard_grads[(int)(id % ft.num_shards)] + (r0 + lane) * E;
+  }
+#pragma unroll
+  for (int s0 = 0; s0 < LPR; ++s0) {
+    const int j = s0 * RPW + rsub;
+    float* q = reinterpret_cast<float*>(__shfl_sync(0xffffffffu, (unsigned long long)dst, j));
+    if (q) {
+      const float4 v = ldg_nc_f4(gout + (r0 + j) * E + sub * 4);
+      *reinterpret_cast<float4*>(q + sub * 4) = v;
     }
   }
 }
@@ -409,8 +457,10 @@ int fill_params(GatherParams& p, const krs_feature_t* features, int F, int64_t B
     KRS_REQUIRE(f.dim > 0 && f.hotness > 0 && f.vocab > 0, "gather: feature %d has bad dim/hotness/vocab", i);
     KRS_REQUIRE(f.combiner >= 0 && f.combiner <= 2, "gather: feature %d has unknown combiner %d", i, f.combiner);
     KRS_REQUIRE(f.out_offset >= 0 && f.out_offset + f.dim <= out_ld, "gather: feature %d columns exceed out_ld", i);
-    KRS_REQUIRE(f.num_shards <= 1 || f.shard_tables != nullptr || f.shard_grads != nullptr,
+    KRS_REQUIRE(f.num_shards <= 1 || (f.shard_mode & 0xff) == KRS_SHARD_OWNER || f.shard_tables != nullptr ||
+                    f.shard_grads != nullptr,
                 "gather: feature %d is sharded but has no shard pointer array", i);
+    KRS_REQUIRE((f.shard_mode & 0xff) <= KRS_SHARD_POSITION, "gather: feature %d has an unknown shard_mode", i);
     p.f[i] = f;
   }
   p.F = F;
@@ -429,7 +479,7 @@ bool uniform_onehot(const GatherParams& p, int* E_out, bool* i64, bool* sharded)
     if (f.hotness != 1 || f.dim != E || f.ids_i64 != is64 || ((f.num_shards > 1) != sh)) return false;
     if (f.weights != nullptr && (f.reduce || f.combiner == KRS_COMBINER_SUM)) return false;
     if (f.out_offset != i * E) return false;
-    if (!sh && (f.table == nullptr || !aligned16(f.table))) return false;
+    if ((!sh || (f.shard_mode & 0xff) == KRS_SHARD_OWNER) && (f.table == nullptr || !aligned16(f.table))) return false;
   }
   *sharded = sh;
   if (p.out_ld != (int64_t)p.F * E || !aligned16(p.out)) return false;
@@ -483,9 +533,13 @@ extern "C" int krs_gather_fwd(const krs_feature_t* features, int F, int64_t B, f
   int rc = fill_params(p, features, F, B, out, out_ld);
   if (rc) return rc;
   KRS_REQUIRE(out != nullptr || B == 0, "krs_gather_fwd: null output");
-  for (int i = 0; i < F; ++i)
-    KRS_REQUIRE(p.f[i].num_shards > 1 ? p.f[i].shard_tables != nullptr : p.f[i].table != nullptr,
+  for (int i = 0; i < F; ++i) {
+    const bool needs_local = p.f[i].num_shards <= 1 || (p.f[i].shard_mode & 0xff) == KRS_SHARD_OWNER;
+    KRS_REQUIRE(needs_local ? p.f[i].table != nullptr : p.f[i].shard_tables != nullptr,
                 "krs_gather_fwd: feature %d has no table", i);
+    KRS_REQUIRE(needs_local || variant != 3 || (p.f[i].shard_mode & 0xff) == KRS_SHARD_DIRECT,
+                "krs_gather_fwd: the generic path only addresses DIRECT sharded tables");
+  }
   if (B == 0) return KRS_OK;
   cudaStream_t s = as_stream(stream);
   int E = 0;
@@ -546,15 +600,38 @@ extern "C" int krs_gather_bwd(const krs_feature_t* features, int F, int64_t B, c
   KRS_REQUIRE(gout != nullptr, "krs_gather_bwd: null gradient");
   bool fast = true;
   const int is64 = p.f[0].ids_i64;
+  const bool push = p.f[0].num_shards > 1 && (p.f[0].shard_mode & 0xff) == KRS_SHARD_POSITION;
   for (int i = 0; i < F; ++i) {
     const krs_feature_t& f = p.f[i];
-    KRS_REQUIRE(f.num_shards > 1 ? f.shard_grads != nullptr : f.grad != nullptr,
+    const bool owner_mode = f.num_shards > 1 && (f.shard_mode & 0xff) == KRS_SHARD_OWNER;
+    KRS_REQUIRE((f.num_shards > 1 && !owner_mode) ? f.shard_grads != nullptr : f.grad != nullptr,
                 "krs_gather_bwd: feature %d has no gradient arena", i);
+    KRS_REQUIRE(((f.num_shards > 1 && (f.shard_mode & 0xff) == KRS_SHARD_POSITION)) == push,
+                "krs_gather_bwd: positional push must be used for all features or none");
     if (f.hotness != 1 || f.ids_i64 != is64) fast = false;
     if (f.weights != nullptr && (f.reduce || f.combiner == KRS_COMBINER_SUM)) fast = false;
   }
   if (B == 0) return KRS_OK;
   cudaStream_t s = as_stream(stream);
+  if (push) {
+    const int E0 = p.f[0].dim;
+    bool ok = fast && (E0 % 4 == 0) && ((E0 / 4) & (E0 / 4 - 1)) == 0 && E0 <= 128 && aligned16(gout) && gout_ld == (int64_t)F * E0;
+    for (int i = 0; i < F && ok; ++i) ok = p.f[i].dim == E0 && p.f[i].out_offset == i * E0;
+    if (!ok) {
+      set_error("krs_gather_bwd: positional push needs 1-hot features of one dim E in {4..128} and a contiguous (B, F*E) gradient");
+      return KRS_EUNSUPPORTED;
+    }
+    const unsigned grid = (unsigned)ceil_div<int64_t>(ceil_div<int64_t>(B * F, 32), 8);
+#define KRS_PUSH(L)                                                                    \
+  case L:                                                                              \
+    if (is64) push_rows_kernel<L, int64_t><<<grid, 256, 0, s>>>(p);                    \
+    else push_rows_kernel<L, int32_t><<<grid, 256, 0, s>>>(p);                         \
+    break;
+    switch (E0 / 4) { KRS_PUSH(1) KRS_PUSH(2) KRS_PUSH(4) KRS_PUSH(8) KRS_PUSH(16) KRS_PUSH(32) }
+#undef KRS_PUSH
+    KRS_LAUNCH_CHECK();
+    return KRS_OK;
+  }
   if (fast) {
     const int64_t items = ceil_div<int64_t>(B, 32) * F;
     const unsigned grid = (unsigned)krs::imax<int64_t>(1, krs::imin<int64_t>(ceil_div<int64_t>(items, 8), 0x7fffffff));

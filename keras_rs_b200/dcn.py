@@ -197,9 +197,8 @@ class DCN(torch.nn.Module):
         b["labels"].copy_(labels.reshape(-1), non_blocking=True)
         s = stream()
         D, P = self.D, (self.P or 0)
-        plan = b["plan"]
         xs = b["xs"]
-        check(lib.krs_gather_fwd(plan.arr, plan.F, B, ptr(xs[0]), D, 0, s))
+        self._gather_into(b, B, s)
         for i, c in enumerate(self.cross):
             x_in = xs[0] if i == 0 else xs[i]
             check(lib.krs_cross_fwd(ptr(xs[0]), ptr(x_in), ptr(c.down_proj_kernel), ptr(c.kernel), ptr(c.bias),
@@ -242,8 +241,17 @@ class DCN(torch.nn.Module):
         if self.L == 0:
             pass
         # cur holds dL/dx0 (B, D): scatter-add into the embedding arena
-        check(lib.krs_gather_bwd(plan.arr, plan.F, B, ptr(cur), D, s))
+        self._scatter_from(b, B, cur, s)
         return b["loss"]
+
+    def _gather_into(self, b, B, s):
+        """Fused multi-table gather of the staged ids into xs[0] (overridden by the row-sharded model)."""
+        plan = b["plan"]
+        check(lib.krs_gather_fwd(plan.arr, plan.F, B, ptr(b["xs"][0]), self.D, 0, s))
+
+    def _scatter_from(self, b, B, cur, s):
+        plan = b["plan"]
+        check(lib.krs_gather_bwd(plan.arr, plan.F, B, ptr(cur), self.D, s))
 
     def train_on_batch(self, ids, labels, optimizer: optimizers.Optimizer, denom: int = 0):
         loss = self.forward_backward(ids, labels, denom)
