@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gather-variant", type=int, default=0)
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     return ap.parse_args()
 
 
@@ -187,8 +188,19 @@ def run_ours(a):
         return ms
 
     # ---- device-resident steps ("value") --------------------------------------------------
+    use_graph = not a.no_graph
+    if use_graph:
+        try:                                           # capture once (also validates NCCL capture on N > 1)
+            model.train_on_batch_graph(dev_ids[0], dev_y[0], opt, denom)
+            torch.cuda.synchronize()
+        except Exception as exc:                       # pragma: no cover
+            if rank == 0:
+                print(f"# CUDA-graph capture unavailable ({type(exc).__name__}: {exc}); eager launches", file=sys.stderr)
+            use_graph = False
+    train = model.train_on_batch_graph if use_graph else model.train_on_batch
+
     def step_dev(i):
-        model.train_on_batch(dev_ids[i % NB], dev_y[i % NB], opt, denom)
+        train(dev_ids[i % NB], dev_y[i % NB], opt, denom)
 
     clocks = Clocks(local)
     if rank == 0:
@@ -202,7 +214,7 @@ def run_ours(a):
     loss_host = torch.zeros((a.steps + a.warmup + 1,), dtype=torch.float32).pin_memory()
 
     def step_e2e(i):
-        loss = model.train_on_batch(host_ids[i % NB], host_y[i % NB], opt, denom)
+        loss = train(host_ids[i % NB], host_y[i % NB], opt, denom)
         loss_host[i % loss_host.numel():i % loss_host.numel() + 1].copy_(loss, non_blocking=True)
 
     ms_e2e = timed(step_e2e, a.steps, 3) / a.steps
@@ -290,11 +302,11 @@ def run_ours(a):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a), "global_batch": B * world, "parallelism": f"dp{world}" + (
             "+mod-row-sharded tables over NVLink peer memory" if world > 1 else ""), "gemm_engine": engine,
-            "l2": "inputs_larger_than_L2", "final_loss": final_loss},
+            "l2": "inputs_larger_than_L2", "final_loss": final_loss, "launch": "cuda_graph" if use_graph else "eager"},
         "clocks": clk,
         "e2e": {"value": e2e_value, "unit": "examples/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4},
-        "gpu_launches": launches_per_step * a.steps,
+        "gpu_launches": launches_per_step * a.steps,   # kernels executed per step x steps (inside one graph replay per step when launch == cuda_graph)
         "roofline": roof, "kernels": kern, "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)

@@ -192,7 +192,12 @@ int krs_loss_fwd_bwd(const float* pred, const float* label, float* loss, float* 
  * without reading them, set rows are read, zeroed and their bit cleared (row_len = floats per row).
  * If touched is NULL, g is read densely and left untouched. */
 int krs_adamw(float* p, float* m, float* v, float* g, uint32_t* touched, int64_t n, int row_len,
-              float lr, float b1, float b2, float eps, float wd, int64_t step, void* stream);
+              float lr, float b1, float b2, float eps, float wd, int64_t step,
+              const float* hyper_dev /* nullable device [lr,b1,b2,eps,wd,alpha,step]: overrides the scalars */,
+              void* stream);
+/* Advances hyper_dev[6] (step) and refreshes hyper_dev[5] (alpha) on the device, so a captured CUDA graph of
+ * the training step can be replayed without per-step host parameters. */
+int krs_adam_hyper_advance(float* hyper_dev, void* stream);
 /* Adagrad (examples/ml_perf/main.py:203): acc += g*g ; p -= lr * g / sqrt(acc + eps).
  * SGD: p -= lr * g.  kind: 0 = SGD, 1 = Adagrad.  Same `touched` arena semantics; with an arena only
  * touched rows are visited (row-sparse update, identical to the dense update for these rules —

@@ -32,7 +32,8 @@ template <bool ARENA>
 __global__ void __launch_bounds__(256) adamw_vec_kernel(float* __restrict__ p, float* __restrict__ m,
                                                         float* __restrict__ v, float* __restrict__ g,
                                                         const uint32_t* __restrict__ touched, int64_t n4, int row_len4,
-                                                        AdamArgs a) {
+                                                        AdamArgs a, const float* __restrict__ hyper) {
+  if (hyper) { a.lr = hyper[0]; a.b1 = hyper[1]; a.b2 = hyper[2]; a.eps = hyper[3]; a.wd = hyper[4]; a.alpha = hyper[5]; }
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 gp = make_float4(0.f, 0.f, 0.f, 0.f);
     if (ARENA) {
@@ -61,7 +62,8 @@ template <bool ARENA>
 __global__ void __launch_bounds__(256) adamw_scalar_kernel(float* __restrict__ p, float* __restrict__ m,
                                                            float* __restrict__ v, float* __restrict__ g,
                                                            const uint32_t* __restrict__ touched, int64_t n, int row_len,
-                                                           AdamArgs a) {
+                                                           AdamArgs a, const float* __restrict__ hyper) {
+  if (hyper) { a.lr = hyper[0]; a.b1 = hyper[1]; a.b2 = hyper[2]; a.eps = hyper[3]; a.wd = hyper[4]; a.alpha = hyper[5]; }
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float gp = 0.f;
     if (ARENA) {
@@ -136,31 +138,40 @@ __global__ void __launch_bounds__(256) dense_sgd_adagrad_kernel(float* __restric
   }
 }
 
+// hyper = [lr, b1, b2, eps, wd, alpha, step]: advances the step counter and refreshes the folded bias
+// correction ON THE DEVICE, so a CUDA-graph replay of the training step needs no per-step host parameters.
+__global__ void adam_hyper_advance_kernel(float* hyper) {
+  const double t = (double)hyper[6] + 1.0;
+  hyper[6] = (float)t;
+  hyper[5] = (float)((double)hyper[0] * sqrt(1.0 - pow((double)hyper[2], t)) / (1.0 - pow((double)hyper[1], t)));
+}
+
 }  // namespace
 }  // namespace krs
 
 using namespace krs;
 
 extern "C" int krs_adamw(float* p, float* m, float* v, float* g, uint32_t* touched, int64_t n, int row_len, float lr,
-                         float b1, float b2, float eps, float wd, int64_t step, void* stream) {
+                         float b1, float b2, float eps, float wd, int64_t step, const float* hyper_dev, void* stream) {
   KRS_REQUIRE(p && m && v && g, "krs_adamw: null argument");
-  KRS_REQUIRE(n >= 0 && step >= 1, "krs_adamw: bad n/step");
+  KRS_REQUIRE(n >= 0 && (step >= 1 || hyper_dev != nullptr), "krs_adamw: bad n/step");
   KRS_REQUIRE(touched == nullptr || (row_len > 0 && n % row_len == 0), "krs_adamw: arena needs n %% row_len == 0");
   if (n == 0) return KRS_OK;
   cudaStream_t s = as_stream(stream);
   AdamArgs a;
   a.lr = lr; a.b1 = b1; a.b2 = b2; a.eps = eps; a.wd = wd;
-  a.alpha = (float)((double)lr * sqrt(1.0 - pow((double)b2, (double)step)) / (1.0 - pow((double)b1, (double)step)));
+  a.alpha = hyper_dev ? 0.f
+                      : (float)((double)lr * sqrt(1.0 - pow((double)b2, (double)step)) / (1.0 - pow((double)b1, (double)step)));
   const bool vec = (n % 4 == 0) && aligned16(p) && aligned16(m) && aligned16(v) && aligned16(g) &&
                    (touched == nullptr || row_len % 4 == 0);
   const int64_t work = vec ? n / 4 : n;
   const unsigned grid = (unsigned)krs::imax<int64_t>(1, krs::imin<int64_t>(ceil_div<int64_t>(work, 256), (int64_t)sm_count() * 32));
   if (vec) {
-    if (touched) adamw_vec_kernel<true><<<grid, 256, 0, s>>>(p, m, v, g, touched, work, row_len / 4, a);
-    else adamw_vec_kernel<false><<<grid, 256, 0, s>>>(p, m, v, g, nullptr, work, 1, a);
+    if (touched) adamw_vec_kernel<true><<<grid, 256, 0, s>>>(p, m, v, g, touched, work, row_len / 4, a, hyper_dev);
+    else adamw_vec_kernel<false><<<grid, 256, 0, s>>>(p, m, v, g, nullptr, work, 1, a, hyper_dev);
   } else {
-    if (touched) adamw_scalar_kernel<true><<<grid, 256, 0, s>>>(p, m, v, g, touched, n, row_len, a);
-    else adamw_scalar_kernel<false><<<grid, 256, 0, s>>>(p, m, v, g, nullptr, n, 1, a);
+    if (touched) adamw_scalar_kernel<true><<<grid, 256, 0, s>>>(p, m, v, g, touched, n, row_len, a, hyper_dev);
+    else adamw_scalar_kernel<false><<<grid, 256, 0, s>>>(p, m, v, g, nullptr, n, 1, a, hyper_dev);
   }
   KRS_LAUNCH_CHECK();
   if (touched) {
@@ -187,6 +198,13 @@ extern "C" int krs_sgd_adagrad(float* p, float* acc, float* g, uint32_t* touched
     const unsigned grid = (unsigned)krs::imax<int64_t>(1, krs::imin<int64_t>(ceil_div<int64_t>(n, 256), (int64_t)sm_count() * 32));
     dense_sgd_adagrad_kernel<<<grid, 256, 0, s>>>(p, acc, g, n, lr, eps, kind);
   }
+  KRS_LAUNCH_CHECK();
+  return KRS_OK;
+}
+
+extern "C" int krs_adam_hyper_advance(float* hyper_dev, void* stream) {
+  KRS_REQUIRE(hyper_dev != nullptr, "krs_adam_hyper_advance: null argument");
+  adam_hyper_advance_kernel<<<1, 1, 0, as_stream(stream)>>>(hyper_dev);
   KRS_LAUNCH_CHECK();
   return KRS_OK;
 }

@@ -195,6 +195,10 @@ class DCN(torch.nn.Module):
         b = self._step_buffers(B)
         b["ids"].copy_(ids, non_blocking=True)
         b["labels"].copy_(labels.reshape(-1), non_blocking=True)
+        return self._run_step(b, B, denom)
+
+    def _run_step(self, b, B: int, denom: int = 0):
+        """Forward + backward on the staged batch (ids / labels already in the static buffers)."""
         s = stream()
         D, P = self.D, (self.P or 0)
         xs = b["xs"]
@@ -257,10 +261,44 @@ class DCN(torch.nn.Module):
         loss = self.forward_backward(ids, labels, denom)
         self._sync_gradients()
         optimizer.iterations += 1
+        if getattr(optimizer, "_hyper_dev", None) is not None:
+            optimizer.advance_device_hyper()       # keep the device-resident step / alpha in lock-step
         with torch.no_grad():
             optimizer._update(self.emb, self.emb_grad, self.emb_touched)
             optimizer._update(self.dense_flat, self.dense_grad_flat, None)
+        self._end_of_step()
         return loss
+
+    def train_on_batch_graph(self, ids, labels, optimizer: optimizers.Optimizer, denom: int = 0):
+        """Same step as train_on_batch, replayed from a CUDA graph captured on first use (per batch size):
+        one graph launch instead of ~45 kernel launches + tensor-map encodes, which removes the host-side gaps
+        between kernels.  Only the H2D copies of ids / labels stay outside the graph."""
+        B = ids.shape[0]
+        b = self._step_buffers(B)
+        key = ("graph", id(optimizer), int(denom))
+        if key not in b:
+            optimizer.enable_device_hyper(self.device_)
+            # warm-up outside capture (lazy one-time initialisation inside the library), then capture
+            self.train_on_batch(ids, labels, optimizer, denom)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._run_step(b, B, denom)
+                self._sync_gradients()
+                optimizer.advance_device_hyper()
+                with torch.no_grad():
+                    optimizer._update(self.emb, self.emb_grad, self.emb_touched)
+                    optimizer._update(self.dense_flat, self.dense_grad_flat, None)
+                self._end_of_step()
+            b[key] = g                         # capturing does not execute: host and device step counters unchanged
+        b["ids"].copy_(ids, non_blocking=True)
+        b["labels"].copy_(labels.reshape(-1), non_blocking=True)
+        b[key].replay()
+        optimizer.iterations += 1
+        return b["loss"]
+
+    def _end_of_step(self):
+        """Hook for cross-rank ordering at the end of a step (row-sharded model)."""
 
     def _sync_gradients(self):
         """Single GPU: nothing to exchange."""

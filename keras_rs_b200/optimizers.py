@@ -39,6 +39,8 @@ class Optimizer:
 
     def apply(self, params: Iterable[torch.Tensor]) -> None:
         self.iterations += 1
+        if getattr(self, "_hyper_dev", None) is not None:
+            self.advance_device_hyper()
         with torch.no_grad():
             for p in params:
                 g, touched = self._grad_of(p)
@@ -47,6 +49,12 @@ class Optimizer:
                 self._update(p, g, touched)
 
     step = apply
+
+    def enable_device_hyper(self, device="cuda"):
+        return None
+
+    def advance_device_hyper(self):
+        pass
 
     def zero_grad(self, params: Iterable[torch.Tensor]) -> None:
         for p in params:
@@ -66,7 +74,20 @@ class AdamW(Optimizer):
         row_len = p.shape[-1] if (touched is not None and p.dim() >= 2) else 1
         check(lib.krs_adamw(ptr(p), ptr(st["m"]), ptr(st["v"]), ptr(g), ptr(touched), p.numel(), row_len,
                             self.learning_rate, self.beta_1, self.beta_2, self.epsilon, self.weight_decay,
-                            self.iterations, stream()))
+                            max(self.iterations, 1), ptr(getattr(self, "_hyper_dev", None)), stream()))
+
+    # ---- device-resident hyper-parameters (CUDA-graph replay of the step) ----
+    def enable_device_hyper(self, device="cuda"):
+        """Keep [lr, b1, b2, eps, wd, alpha, step] on the device; `advance_device_hyper()` (a 1-thread kernel)
+        then replaces the host-side step counter, so a captured step needs no per-replay parameters."""
+        if getattr(self, "_hyper_dev", None) is None:
+            self._hyper_dev = torch.tensor([self.learning_rate, self.beta_1, self.beta_2, self.epsilon,
+                                            self.weight_decay, 0.0, float(self.iterations)], dtype=torch.float32,
+                                           device=device)
+        return self._hyper_dev
+
+    def advance_device_hyper(self):
+        check(lib.krs_adam_hyper_advance(ptr(self._hyper_dev), stream()))
 
 
 class Adam(AdamW):

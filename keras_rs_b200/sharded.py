@@ -182,6 +182,8 @@ class ShardedDCN(DCN):
         for r in range(S):                                            # 4. owner side (local atomics)
             pb = b["owner_bwd"][r]
             check(lib.krs_gather_bwd(pb.arr, F, B, b["gstage"][r].data_ptr(), D, s))
+
+    def _end_of_step(self):
         self._barrier()                                               # peers are done with my ids / staging
 
     def _sync_gradients(self):

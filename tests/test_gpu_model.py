@@ -173,3 +173,24 @@ def test_c2_full_size_gather_properties():
         pop += int((x & 1).sum())
         x >>= 1
     assert pop == uniq
+
+
+@pytest.mark.parametrize("opt_name", ["adamw", "adagrad"])
+def test_cuda_graph_step_matches_eager_step(opt_name):
+    """train_on_batch_graph (one CUDA-graph replay per step, device-resident Adam step/alpha) must produce the
+    same parameters as the eager launch sequence."""
+    import keras_rs_b200 as K
+    rng = np.random.default_rng(9)
+    vocab, E, B = [64, 40, 33], 32, 128
+    mk_opt = (lambda: K.optimizers.AdamW(0.01)) if opt_name == "adamw" else (lambda: K.optimizers.Adagrad(0.05))
+    m1, m2 = _mk(vocab, E, 2, None, (16,), seed=4), _mk(vocab, E, 2, None, (16,), seed=4)
+    o1, o2 = mk_opt(), mk_opt()
+    for step in range(5):
+        ids = np.stack([rng.integers(0, v, size=B) for v in vocab], axis=1).astype(np.int32)
+        y = rng.uniform(size=B).astype(np.float32)
+        l1 = float(m1.train_on_batch(dev(ids), dev(y), o1))
+        l2 = float(m2.train_on_batch_graph(dev(ids), dev(y), o2))
+        np.testing.assert_allclose(l1, l2, rtol=1e-6)
+    assert o1.iterations == o2.iterations == 5
+    assert_close(npy(m2.emb), npy(m1.emb), rel=1e-6, what="emb after 5 graph steps")
+    assert_close(npy(m2.dense_flat), npy(m1.dense_flat), rel=1e-6, what="dense params after 5 graph steps")
