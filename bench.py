@@ -273,6 +273,47 @@ def run_ours(a):
         kern["gather_bwd"] = {"ms": ms_s, "GBps": (B * F * E * 4 * 3 + B * F * 4) / ms_s * 1e-6}
         base.emb_grad.zero_(); base.emb_touched.zero_()
 
+    # ---- in-situ per-call profile of the eager step (CUDA events around every C-ABI call) -------------------
+    step_profile = None
+    if world == 1:
+        import collections
+        names = ["krs_gather_fwd", "krs_cross_fwd", "krs_dense_fwd", "krs_loss_fwd_bwd", "krs_dense_bwd", "krs_cross_bwd",
+                 "krs_gather_bwd", "krs_adamw", "krs_sgd_adagrad", "krs_adam_hyper_advance"]
+        recs = []
+        orig = {n: getattr(lib, n) for n in names}
+
+        def wrap(n, fn):
+            def f(*args):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                rc = fn(*args)
+                e1.record()
+                recs.append((n, e0, e1))
+                return rc
+            return f
+
+        for n in names:
+            setattr(lib, n, wrap(n, orig[n]))
+        try:
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for i in range(2):
+                base.train_on_batch(dev_ids[i % NB], dev_y[i % NB], opt, denom)
+            recs.clear()
+            t0.record()
+            for i in range(3):
+                base.train_on_batch(dev_ids[i % NB], dev_y[i % NB], opt, denom)
+            t1.record()
+            torch.cuda.synchronize()
+            agg = collections.OrderedDict()
+            for n, e0, e1 in recs:
+                agg[n] = agg.get(n, 0.0) + e0.elapsed_time(e1) / 3
+            step_profile = {k: round(v, 3) for k, v in agg.items()}
+            step_profile["sum_of_calls"] = round(sum(agg.values()), 3)
+            step_profile["step_wall"] = round(t0.elapsed_time(t1) / 3, 3)
+        finally:
+            for n in names:
+                setattr(lib, n, orig[n])
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -307,7 +348,7 @@ def run_ours(a):
         "e2e": {"value": e2e_value, "unit": "examples/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4},
         "gpu_launches": launches_per_step * a.steps,   # kernels executed per step x steps (inside one graph replay per step when launch == cuda_graph)
-        "roofline": roof, "kernels": kern, "cpu_baseline": cpu,
+        "roofline": roof, "kernels": kern, "step_profile_ms": step_profile, "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -278,8 +278,9 @@ class DCN(torch.nn.Module):
         key = ("graph", id(optimizer), int(denom))
         if key not in b:
             optimizer.enable_device_hyper(self.device_)
-            # warm-up outside capture (lazy one-time initialisation inside the library), then capture
-            self.train_on_batch(ids, labels, optimizer, denom)
+            # this batch's step runs eagerly (it also performs the library's lazy one-time initialisation);
+            # the graph captured right after it serves every later batch of this size
+            loss = self.train_on_batch(ids, labels, optimizer, denom)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
@@ -291,6 +292,7 @@ class DCN(torch.nn.Module):
                     optimizer._update(self.dense_flat, self.dense_grad_flat, None)
                 self._end_of_step()
             b[key] = g                         # capturing does not execute: host and device step counters unchanged
+            return loss
         b["ids"].copy_(ids, non_blocking=True)
         b["labels"].copy_(labels.reshape(-1), non_blocking=True)
         b[key].replay()
