@@ -35,16 +35,16 @@ __global__ void __launch_bounds__(256) adamw_vec_kernel(float* __restrict__ p, f
                                                         AdamArgs a, const float* __restrict__ hyper) {
   if (hyper) { a.lr = hyper[0]; a.b1 = hyper[1]; a.b2 = hyper[2]; a.eps = hyper[3]; a.wd = hyper[4]; a.alpha = hyper[5]; }
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-    float4 gp = make_float4(0.f, 0.f, 0.f, 0.f);
+    // ALL loads first, the re-zeroing store of the gradient row last: with `g = load; store 0` ahead of the
+    // p/m/v loads the same-address store serialised a second DRAM round trip per thread (probe: 3.2 ms with no
+    // touched rows, 5.9 ms at 6.5 %, 13.9 ms at 100 % — benchmarks/adamw_probe.py)
+    bool hit = !ARENA;
     if (ARENA) {
       const int64_t row = i / row_len4;
-      if ((touched[row >> 5] >> (row & 31)) & 1u) {
-        gp = reinterpret_cast<float4*>(g)[i];
-        reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    } else {
-      gp = reinterpret_cast<const float4*>(g)[i];
+      hit = (touched[row >> 5] >> (row & 31)) & 1u;
     }
+    float4 gp = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (hit) gp = reinterpret_cast<const float4*>(g)[i];
     float4 pp = reinterpret_cast<float4*>(p)[i];
     float4 mm = reinterpret_cast<float4*>(m)[i];
     float4 vv = reinterpret_cast<float4*>(v)[i];
@@ -55,6 +55,7 @@ __global__ void __launch_bounds__(256) adamw_vec_kernel(float* __restrict__ p, f
     reinterpret_cast<float4*>(p)[i] = pp;
     reinterpret_cast<float4*>(m)[i] = mm;
     reinterpret_cast<float4*>(v)[i] = vv;
+    if (ARENA && hit) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 
@@ -65,21 +66,18 @@ __global__ void __launch_bounds__(256) adamw_scalar_kernel(float* __restrict__ p
                                                            AdamArgs a, const float* __restrict__ hyper) {
   if (hyper) { a.lr = hyper[0]; a.b1 = hyper[1]; a.b2 = hyper[2]; a.eps = hyper[3]; a.wd = hyper[4]; a.alpha = hyper[5]; }
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    float gp = 0.f;
+    bool hit = !ARENA;
     if (ARENA) {
       const int64_t row = i / row_len;
-      if ((touched[row >> 5] >> (row & 31)) & 1u) {
-        gp = g[i];
-        g[i] = 0.f;
-      }
-    } else {
-      gp = g[i];
+      hit = (touched[row >> 5] >> (row & 31)) & 1u;
     }
+    float gp = hit ? g[i] : 0.f;
     float pp = p[i], mm = m[i], vv = v[i];
     adamw_one(pp, mm, vv, gp, a);
     p[i] = pp;
     m[i] = mm;
     v[i] = vv;
+    if (ARENA && hit) g[i] = 0.f;
   }
 }
 
@@ -107,15 +105,16 @@ __global__ void __launch_bounds__(256) sparse_rows_kernel(float* __restrict__ p,
         if (row >= nrows) break;
         const int64_t base = row * (int64_t)row_len;
         for (int c = lane; c < row_len; c += 32) {
-          const float gg = g[base + c];
-          g[base + c] = 0.f;
+          const float gg = g[base + c];                 // loads first, re-zeroing store last (see adamw_vec_kernel)
+          const float pv = p[base + c];
           if (kind == 1) {
             const float a2 = acc[base + c] + gg * gg;
             acc[base + c] = a2;
-            p[base + c] = p[base + c] - lr * gg / sqrtf(a2 + eps);
+            p[base + c] = pv - lr * gg / sqrtf(a2 + eps);
           } else {
-            p[base + c] = p[base + c] - lr * gg;
+            p[base + c] = pv - lr * gg;
           }
+          g[base + c] = 0.f;
         }
       }
     }
