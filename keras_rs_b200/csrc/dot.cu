@@ -71,10 +71,16 @@ __global__ void __launch_bounds__(128) dot_fwd_mma_kernel(const __grid_constant_
       for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
         for (int q = 0; q < 4; ++q) acc[mt][nt][q] = 0.f;
-    for (int k0 = 0; k0 < E; k0 += 16) {
-      float4 x[4];
+    // software pipeline: the next 16-wide k chunk is in flight while the current one feeds the tensor core
+    // (the mma asm blocks are volatile, so the compiler would not hoist the loads by itself; with one chunk in
+    // flight per warp the kernel reached only 46 % of the HBM roofline)
+    float4 x[4], xn[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) x[i] = rp[i] ? ldg_nc_f4(rp[i] + k0) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < 4; ++i) x[i] = rp[i] ? ldg_nc_f4(rp[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k0 = 0; k0 < E; k0 += 16) {
+      const bool more = k0 + 16 < E;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) xn[i] = (more && rp[i]) ? ldg_nc_f4(rp[i] + k0 + 16) : make_float4(0.f, 0.f, 0.f, 0.f);
       // two k8 steps per 16-wide chunk: step 0 uses (.x,.y) as k slots (t, t+4); step 1 uses (.z,.w)
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
@@ -95,6 +101,8 @@ __global__ void __launch_bounds__(128) dot_fwd_mma_kernel(const __grid_constant_
             mma_tf32(acc[mt][nt], hi[2 * mt][0], hi[2 * mt + 1][0], hi[2 * mt][1], hi[2 * mt + 1][1], hi[nt][0], hi[nt][1]);
           }
       }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) x[i] = xn[i];
     }
     float* o = p.out + b * (int64_t)p.out_dim;
 #pragma unroll

@@ -98,8 +98,9 @@ def synthetic_c2(F=26, V=1_000_000, E=32, L=3, units=(192, 192), seed=1234):
 
 
 def time_cpu_baseline(B=65536, F=26, V=1_000_000, E=32, L=3, units=(192, 192), steps=3, warmup=1, optimizer="adamw",
-                      threads=None, seed=1234):
-    """examples/s of the CPU restatement on this host.  Returns dict(value, cores, steps, ms_per_step)."""
+                      threads=None, seed=1234, budget_s=None):
+    """examples/s of the CPU restatement on this host.  Returns dict(value, cores, steps, ms_per_step).
+    budget_s bounds the wall time: timed steps stop once the budget is spent (at least one is always run)."""
     import os
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
@@ -107,6 +108,7 @@ def time_cpu_baseline(B=65536, F=26, V=1_000_000, E=32, L=3, units=(192, 192), s
     model = TorchDCN(tables, cross, mlp, lr=0.01, optimizer=optimizer)
     g = torch.Generator().manual_seed(seed + 1)
     times = []
+    t_start = time.perf_counter()
     for s in range(warmup + steps):
         ids = torch.randint(0, V, (B, F), generator=g)
         y = torch.rand((B,), generator=g)
@@ -115,5 +117,7 @@ def time_cpu_baseline(B=65536, F=26, V=1_000_000, E=32, L=3, units=(192, 192), s
         dt = time.perf_counter() - t0
         if s >= warmup:
             times.append(dt)
+        if budget_s is not None and times and (time.perf_counter() - t_start) + dt > budget_s:
+            break
     sec = sum(times) / len(times)
-    return dict(value=B / sec, cores=threads, steps=steps, ms_per_step=sec * 1e3, batch=B)
+    return dict(value=B / sec, cores=threads, steps=len(times), warmup=min(warmup, s), ms_per_step=sec * 1e3, batch=B)

@@ -120,3 +120,20 @@ def test_tc_full_size_accuracy_c2_shapes(tc):
         scale = float(ref.abs().max())
         assert err <= 1e-5 * scale, f"{what}: max abs err {err:.3e} > 1e-5 * {scale:.3e}"
         print(f"tc accuracy {what}: max abs err / max|ref| = {err / scale:.2e}")
+
+
+def test_tc_mlperf_dcnv2_shape_low_rank(tc):
+    """examples/ml_perf shape (DLRM-DCNv2): D = 3456, projection_dim = 512 (ml_perf/model.py:317-325).  The down
+    projection reduces over K = 3456 > 1024, i.e. the K-split + fp32 RED path; compared with float64 on device."""
+    g = torch.Generator(device="cuda").manual_seed(3)
+    B, D, P = 1024, 3456, 512
+    x0 = torch.randn((B, D), device="cuda", generator=g)
+    x = torch.randn((B, D), device="cuda", generator=g)
+    layer = tc.layers.FeatureCross(projection_dim=P)
+    before = _count(tc)
+    y = layer(x0, x)
+    assert _count(tc) >= before + 2
+    U, V, b = layer.down_proj_kernel.detach().double(), layer.kernel.detach().double(), layer.bias.detach().double()
+    ref = x0.double() * ((x.double() @ U) @ V + b) + x.double()
+    err = float((y.double() - ref).abs().max() / ref.abs().max())
+    assert err <= 1e-5, err
