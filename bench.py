@@ -45,13 +45,17 @@ def parse():
     ap.add_argument("--cpu-budget-s", type=float, default=150.0, help="wall-time bound of the CPU legs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gather-variant", type=int, default=0)
-    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--graph", action="store_true", help="replay the step from a CUDA graph (1 GPU; the eager step already has no launch gaps)")
+    ap.add_argument("--projection-dim", type=int, default=0, help="low-rank FeatureCross (ml_perf uses 512); 0 = full rank")
+    ap.add_argument("--dense-units", default="192,192")
     return ap.parse_args()
 
 
 def workload_name(a):
+    rank_s = f"low-rank P={a.projection_dim}" if a.projection_dim else "full-rank"
     return (f"DCN-v2 C2: {a.features} categorical features, vocab {a.vocab} each, embed_dim={a.embed_dim}, "
-            f"batch={a.batch}, {a.cross_layers} full-rank cross layers, Dense 192-192-1, MSE, {a.optimizer}")
+            f"batch={a.batch}, {a.cross_layers} {rank_s} cross layers, Dense {a.dense_units.replace(',', '-')}-1, MSE, "
+            f"{a.optimizer}")
 
 
 # --------------------------------------------------------------------------------------- reference arm
@@ -144,6 +148,8 @@ def run_ours(a):
     K.set_gemm_engine(engine)
 
     B, F, V, E, L = a.batch, a.features, a.vocab, a.embed_dim, a.cross_layers
+    units = tuple(int(u) for u in a.dense_units.split(",") if u)
+    proj = a.projection_dim or None
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -154,10 +160,10 @@ def run_ours(a):
 
     if world > 1:
         from keras_rs_b200.sharded import ShardedDCN
-        model = ShardedDCN([V] * F, embedding_dim=E, num_cross_layers=L, dense_units=(192, 192), seed=1234, rank=rank,
-                           world=world)
+        model = ShardedDCN([V] * F, embedding_dim=E, num_cross_layers=L, dense_units=units, projection_dim=proj,
+                           seed=1234, rank=rank, world=world)
     else:
-        model = DCN([V] * F, embedding_dim=E, num_cross_layers=L, dense_units=(192, 192), seed=1234)
+        model = DCN([V] * F, embedding_dim=E, num_cross_layers=L, dense_units=units, projection_dim=proj, seed=1234)
     opt = {"adamw": lambda: K.optimizers.AdamW(0.01), "adagrad": lambda: K.optimizers.Adagrad(0.01),
            "sgd": lambda: K.optimizers.SGD(0.01)}[a.optimizer]()
 
@@ -193,7 +199,7 @@ def run_ours(a):
         return ms
 
     # ---- device-resident steps ("value") --------------------------------------------------
-    use_graph = not a.no_graph
+    use_graph = a.graph and world == 1
     if use_graph:
         try:                                           # capture once (also validates NCCL capture on N > 1)
             model.train_on_batch_graph(dev_ids[0], dev_y[0], opt, denom)
@@ -251,13 +257,14 @@ def run_ours(a):
         kern["gather_fwd"] = {"ms": ms_g, "GBps": gather_bytes / ms_g * 1e-6, "bytes": gather_bytes}
         c0 = base.cross[0]
         x0, x1, h2 = bufs["xs"][0], bufs["xs"][1], bufs["h2"][0]
+        hp0 = bufs["hproj"][0]
 
         def cross_i(i):
-            check(lib.krs_cross_fwd(ptr(x0), ptr(x0), None, ptr(c0.kernel), ptr(c0.bias), 0.0, 0, ptr(x1), ptr(h2), None,
-                                    None, B, base.D, 0, s))
+            check(lib.krs_cross_fwd(ptr(x0), ptr(x0), ptr(c0.down_proj_kernel), ptr(c0.kernel), ptr(c0.bias), 0.0, 0, ptr(x1),
+                                    ptr(h2), None, ptr(hp0), B, base.D, proj or 0, s))
 
         ms_c = timed(cross_i, 5, 2) / 5
-        flops = 2.0 * B * base.D * base.D
+        flops = 4.0 * B * base.D * proj if proj else 2.0 * B * base.D * base.D
         kern["cross_fwd"] = {"ms": ms_c, "TFLOPs": flops / ms_c * 1e-9, "flops": flops, "engine": engine}
 
         def adamw_i(i):
@@ -337,7 +344,8 @@ def run_ours(a):
                          "(torch-CPU restatement of the Keras op sequence on all host cores; keras/jax not installable "
                          "here)", "ms_per_step": r["ms_per_step"]}
 
-    launches_per_step = 1 + L + 3 + 1 + 3 * 3 + 3 * L + 1 + 2
+    n_mlp = len(units) + 1
+    launches_per_step = 1 + L * (2 if proj else 1) + n_mlp + 1 + 3 * n_mlp + L * (5 if proj else 3) + 1 + 2
     roof = None
     if kern:
         gk = kern["gather_fwd"]

@@ -9,6 +9,12 @@ from . import _lib  # noqa: F401  (raises ImportError when the CUDA extension is
 from . import initializers, layers, ops, optimizers  # noqa: F401
 from .ops import get_gemm_engine, set_gemm_engine  # noqa: F401
 
+import os as _os
+
+# dense contractions: tensor pipe (tcgen05, 3xTF32 split, fp32-level accuracy) unless KRS_GEMM_ENGINE=ffma asks
+# for the exact-fp32 FMA engine.  Shapes the tensor-core kernel does not take fall through to FFMA automatically.
+set_gemm_engine(_os.environ.get("KRS_GEMM_ENGINE", "tcgen05"))
+
 __version__ = "0.1.0"
 
 

@@ -24,3 +24,13 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(autouse=True)
+def _pin_exact_engine(request):
+    """GPU parity tests run on the exact-fp32 FFMA engine unless they ask for the `tc` fixture
+    (tests/test_gpu_tc.py), so tolerances do not depend on which engine is the package default."""
+    if "gpu" in request.keywords:
+        import keras_rs_b200 as K
+        K.set_gemm_engine("ffma")
+    yield
