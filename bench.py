@@ -270,9 +270,10 @@ def run_ours(a):
         def adamw_i(i):
             opt._update(base.emb, base.emb_grad, base.emb_touched)
 
-        ms_a = timed(adamw_i, 5, 2) / 5
-        adam_bytes = base.emb.numel() * 4 * 6
-        kern["adamw_tables"] = {"ms": ms_a, "GBps": adam_bytes / ms_a * 1e-6, "bytes": adam_bytes}
+        if a.optimizer == "adamw":     # dense-exact sweep: p, m, v read + written, g read + re-zeroed
+            ms_a = timed(adamw_i, 5, 2) / 5
+            adam_bytes = base.emb.numel() * 4 * 6
+            kern["adamw_tables"] = {"ms": ms_a, "GBps": adam_bytes / ms_a * 1e-6, "bytes": adam_bytes}
 
         def scatter_i(i):
             p = plans[i % NB]
