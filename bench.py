@@ -35,7 +35,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--optimizer", default="adamw", choices=["adamw", "adagrad", "sgd"])
-    ap.add_argument("--engine", default="auto", choices=["auto", "ffma", "tcgen05"])
+    ap.add_argument("--engine", default="auto", choices=["auto", "ffma", "tcgen05", "tcgen05_ts"])
     ap.add_argument("--batch", type=int, default=65536)
     ap.add_argument("--features", type=int, default=26)
     ap.add_argument("--vocab", type=int, default=1_000_000)
@@ -347,12 +347,35 @@ def run_ours(a):
 
     n_mlp = len(units) + 1
     launches_per_step = 1 + L * (2 if proj else 1) + n_mlp + 1 + 3 * n_mlp + L * (5 if proj else 3) + 1 + 2
-    roof = None
+    # ncu-measured DRAM traffic per launch of the two kernels below (profiles/ncu_traffic.json, written from the
+    # committed `ncu --set full` captures by profiles/summarize.py; null when no capture of that kernel is committed)
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception:
+        pass
+    roof = roof_gather = None
     if kern:
         gk = kern["gather_fwd"]
-        roof = {"kernel": "gather_fast_kernel (fused 26-table gather+concat)", "bound": "hbm", "achieved": gk["GBps"],
-                "peak": hbm_peak, "unit": "GB/s", "frac": gk["GBps"] / hbm_peak, "frac_of_8TBps_nominal": gk["GBps"] / 8000.0,
-                "peak_source": peak_src, "traffic": None, "algorithmic_bytes": gk["bytes"], "ms": gk["ms"]}
+        roof_gather = {"kernel": "gather_fast_kernel (fused 26-table gather+concat)", "bound": "hbm", "achieved": gk["GBps"],
+                       "peak": hbm_peak, "unit": "GB/s", "frac": gk["GBps"] / hbm_peak,
+                       "frac_of_8TBps_nominal": gk["GBps"] / 8000.0, "peak_source": peak_src,
+                       "traffic": (traffic.get("gather_fast_kernel") or {}).get("dram_bytes"),
+                       "algorithmic_bytes": gk["bytes"], "ms": gk["ms"]}
+        # the dominant kernel of the step is the dense contraction (gemm_tc_kernel: ~60 % of the step's device time,
+        # profiles/r1_launches_tcgen05.md).  Algorithmic flops = 2*B*D*D per full-rank cross layer; the
+        # kernel issues 3 TF32 MMAs per product for fp32-level accuracy, so its tensor peak is the measured dense bf16
+        # rate / 2 (tf32) / 3 (split) = bf16 / 6 — the burst figure, since this launch is timed alone.
+        ck = kern["cross_fwd"]
+        bf16_peak = float(peaks.get("bf16_tflops", 1590.0))
+        tpeak = bf16_peak / 6.0 if engine != "ffma" else None
+        roof = {"kernel": ("gemm_tc_kernel" if engine != "ffma" else "sgemm_kernel") + " (FeatureCross forward: x@W + fused cross epilogue)",
+                "bound": "tensor", "achieved": ck["TFLOPs"], "peak": tpeak, "unit": "TFLOP/s",
+                "frac": (ck["TFLOPs"] / tpeak) if tpeak else None,
+                "peak_source": ("measured bf16 burst %.0f TF/s (MEASURED_PEAKS.json) / 6 for the 3xTF32 split" % bf16_peak)
+                if "bf16_tflops" in peaks else "fallback 1590 TF/s bf16 / 6",
+                "algorithmic_flops": ck["flops"], "ms": ck["ms"], "engine": engine,
+                "traffic": (traffic.get("gemm_tc_kernel") or {}).get("dram_bytes")}
     line = {
         "metric": "examples/sec", "value": value, "unit": "examples/s", "n_gpus": world, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -364,7 +387,7 @@ def run_ours(a):
         "e2e": {"value": e2e_value, "unit": "examples/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4},
         "gpu_launches": launches_per_step * a.steps,   # kernels executed per step x steps (inside one graph replay per step when launch == cuda_graph)
-        "roofline": roof, "kernels": kern, "step_profile_ms": step_profile, "cpu_baseline": cpu,
+        "roofline": roof, "roofline_gather": roof_gather, "kernels": kern, "step_profile_ms": step_profile, "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -32,8 +32,9 @@ int sm_count() {
 int gemm(const float* A, int64_t lda, bool transA, const float* B, int64_t ldb, bool transB, float* C,
          int64_t ldc, int64_t M, int64_t N, int64_t K, const Epilogue& epi, int split_k, bool accumulate,
          cudaStream_t stream) {
-  if (g_engine.load() == 1) {
-    int rc = gemm_tc(A, lda, transA, B, ldb, transB, C, ldc, M, N, K, epi, split_k, accumulate, stream);
+  const int eng = g_engine.load();
+  if (eng == 1 || eng == 2) {
+    int rc = gemm_tc(A, lda, transA, B, ldb, transB, C, ldc, M, N, K, epi, split_k, accumulate, stream, eng);
     if (rc != KRS_EUNSUPPORTED) return rc;
   }
   return gemm_ffma(A, lda, transA, B, ldb, transB, C, ldc, M, N, K, epi, split_k, accumulate, stream);
@@ -45,8 +46,8 @@ int krs_version(void) { return 100; }
 const char* krs_last_error(void) { return krs::g_err; }
 int krs_device_sm_count(void) { return krs::sm_count(); }
 int krs_set_gemm_engine(int engine) {
-  if (engine != 0 && engine != 1) {
-    krs::set_error("krs_set_gemm_engine: engine must be 0 (ffma) or 1 (tcgen05), got %d", engine);
+  if (engine < 0 || engine > 2) {
+    krs::set_error("krs_set_gemm_engine: engine must be 0 (ffma), 1 (tcgen05, SS operands) or 2 (tcgen05, A in TMEM), got %d", engine);
     return KRS_EINVAL;
   }
   krs::g_engine.store(engine);

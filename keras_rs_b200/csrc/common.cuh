@@ -105,7 +105,7 @@ int gemm_ffma(const float* A, int64_t lda, bool transA, const float* B, int64_t 
 // returns KRS_EUNSUPPORTED when the shape/alignment is outside what the tcgen05 kernel handles
 int gemm_tc(const float* A, int64_t lda, bool transA, const float* B, int64_t ldb, bool transB, float* C,
             int64_t ldc, int64_t M, int64_t N, int64_t K, const Epilogue& epi, int split_k, bool accumulate,
-            cudaStream_t stream);
+            cudaStream_t stream, int ver = 1);
 int pick_split_k(int64_t M, int64_t N, int64_t K);
 
 }  // namespace krs

@@ -56,6 +56,17 @@ constexpr int EPI_SMEM_BYTES = 4 * 32 * EPI_LD * 4;   // one 32x32 staging tile 
 constexpr int A_BYTES = BM * BK * 4;             // 8192
 constexpr int KC_MAX = 1024;                     // max K elements accumulated inside one TMEM tile
 constexpr int SPIN_LIMIT = 1 << 26;              // turns a protocol bug into a trap instead of a hang
+// Kernel versions.  VER 1: both operands read by the tensor core from shared memory (SS), converters write
+// A_lo / B_lo tiles to shared memory.  VER 2: the A operand (hi and lo) lives in TENSOR MEMORY (TS): converter
+// threads own one tile row each, read it from the TMA-landed raw tile, split it in registers and tcgen05.st the
+// two halves into a 4-deep TMEM ring, so A never crosses the shared-memory port again (VER 1 spends 8 KB of
+// writes + 3 x 8 KB of UMMA operand reads per k-block on it; the shared-memory pipe was the measured limiter,
+// profiles/r1_gemm_tc_clock_trace.txt).  TMEM: 2 x (main + cross) x 96 accumulator columns + 4 x 32 A columns.
+template <int VER> struct Cfg {
+  static constexpr int ACC_BN = VER == 2 ? 96 : 128;   // max N tile == accumulator width
+  static constexpr int A_COL0 = 4 * ACC_BN;            // VER 2: first TMEM column of the A ring
+  static constexpr int SA = 4;                         // VER 2: A ring depth (32 columns each: hi | lo)
+};
 
 std::atomic<long long> g_tc_launches{0};
 std::atomic<unsigned long long*> g_trace{nullptr};
@@ -76,6 +87,7 @@ struct TcArgs {
   int epi_vec;            // rows of C / h2 / z / aux streams are 16-byte aligned (vector epilogue)
   int no_mask;            // 1: leave hi = raw fp32 bits (hardware ignores the low 13 mantissa bits)
   int mn_lbo, mn_sbo, mn_kstep, mn_layout;   // MN-major descriptor strides (bytes) and UMMA layout type
+  int fuse_n;             // VER 2: one N = 2*bn MMA computes A_hi x [B_hi | B_lo] (main and hi*lo terms together)
   Epilogue epi;
 };
 
@@ -172,6 +184,25 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, ui
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// A operand from tensor memory (lane = tile row, one 32-bit column per k element), B by shared-memory descriptor
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -284,8 +315,11 @@ __device__ __forceinline__ void epilogue_scalar(const TcArgs& g, int64_t m, int6
 }
 
 // ---------------------------------------------------------------- the kernel
+template <int VER>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const TcArgs g) {
+  constexpr int ACC_BN = Cfg<VER>::ACC_BN;
+  constexpr int SA = Cfg<VER>::SA;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // carve: stages first (1024-aligned), then barriers
   // align by OFFSET (not by integer round trip) so the compiler keeps the shared address space (LDS/STS,
@@ -293,7 +327,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int b_bytes = g.bn * BK * 4;
   const int raw_bytes = A_BYTES + b_bytes;
-  const int stage_bytes = 2 * raw_bytes;
+  const int stage_bytes = VER == 2 ? raw_bytes + b_bytes : 2 * raw_bytes;   // VER 2: A_raw | B_raw | B_lo
+  const int blo_off = VER == 2 ? raw_bytes : raw_bytes + A_BYTES;             // B_lo tile inside a stage
+  const int cross_off = VER == 2 ? g.bn : ACC_BN;                             // cross-term accumulator = main + cross_off
   const int STAGES = g.stages;
   float* epi_stage = reinterpret_cast<float*>(smem + (size_t)STAGES * stage_bytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * stage_bytes + EPI_SMEM_BYTES);
@@ -303,6 +339,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   uint64_t* tmem_full = bars + 3 * MAX_STAGES;   // [1]
   uint64_t* tmem_empty = bars + 3 * MAX_STAGES + 2;  // [1]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + 4);
+  uint64_t* afree_bar = bars + 3 * MAX_STAGES + 5;   // [SA] VER 2: MMAs that read the TMEM A stage have completed
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -311,13 +348,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&conv_bar[s], NUM_CONV_THREADS / 32);   // one arrival per converter warp
+      mbar_init(&conv_bar[s], VER == 2 ? 4 : NUM_CONV_THREADS / 32);   // one arrival per converter warp (VER 2: per group)
       mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], 4);    // one arrival per epilogue warp
     }
+    if (VER == 2)
+      for (int a = 0; a < SA; ++a) mbar_init(&afree_bar[a], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == W_MMA) {
@@ -387,7 +426,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const uint64_t dA_hi = g.a_mn_major ? desc_mnmajor(s0, 0, g) : desc_kmajor(s0, 0);
     const uint64_t dA_lo = g.a_mn_major ? desc_mnmajor(s0 + raw_bytes, 0, g) : desc_kmajor(s0 + raw_bytes, 0);
     const uint64_t dB_hi = g.b_mn_major ? desc_mnmajor(s0 + A_BYTES, 0, g) : desc_kmajor(s0 + A_BYTES, 0);
-    const uint64_t dB_lo = g.b_mn_major ? desc_mnmajor(s0 + A_BYTES + raw_bytes, 0, g) : desc_kmajor(s0 + A_BYTES + raw_bytes, 0);
+    const uint64_t dB_lo = g.b_mn_major ? desc_mnmajor(s0 + blo_off, 0, g) : desc_kmajor(s0 + blo_off, 0);
+    const uint32_t idesc_ts = idesc & ~(1u << 15);                                           // TMEM A is K-major
+    const uint32_t idesc_ts2 = (idesc_ts & ~(0x3Fu << 17)) | ((uint32_t)((2 * g.bn) >> 3) << 17);   // N = 2*bn
+    int astage = 0;
     const uint32_t a_kstep16 = (uint32_t)(g.a_mn_major ? g.mn_kstep : 32) >> 4;
     const uint32_t b_kstep16 = (uint32_t)(g.b_mn_major ? g.mn_kstep : 32) >> 4;
     for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -396,8 +438,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int64_t kb1 = imin<int64_t>(g.kblocks_total, kb0 + g.kblocks_per_split);
       mbar_wait_relaxed(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
-      const uint32_t d_main = tmem_base + (uint32_t)(acc * 2 * MAX_BN);
-      const uint32_t d_small = d_main + (uint32_t)MAX_BN;
+      const uint32_t d_main = tmem_base + (uint32_t)(acc * 2 * ACC_BN);
+      const uint32_t d_small = d_main + (uint32_t)cross_off;
       for (int64_t kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&conv_bar[stage], phase);
         tc_fence_after();
@@ -406,16 +448,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           // descriptors = per-launch base (stage 0, k-step 0) + (stage offset + k-step offset) >> 4 in the
           // 14-bit start-address field: one 32-bit add each instead of rebuilding the bit fields
           const uint32_t so = (uint32_t)(stage * stage_bytes) >> 4;
+          if constexpr (VER == 2) {
+            const uint32_t ta_hi = tmem_base + (uint32_t)(Cfg<VER>::A_COL0 + astage * 32);   // lanes 0..127
+            const uint32_t ta_lo = ta_hi + 16;
 #pragma unroll
-          for (int ks = 0; ks < BK / 8; ++ks) {
-            const uint64_t dah = dA_hi + so + (ks ? a_kstep16 : 0u);
-            const uint64_t dal = dA_lo + so + (ks ? a_kstep16 : 0u);
-            const uint64_t dbh = dB_hi + so + (ks ? b_kstep16 : 0u);
-            const uint64_t dbl = dB_lo + so + (ks ? b_kstep16 : 0u);
-            const uint32_t first = (kb == kb0 && ks == 0) ? 0u : 1u;
-            tc_mma_tf32(d_small, dal, dbh, idesc, first);    // cross terms: their own accumulator
-            tc_mma_tf32(d_small, dah, dbl, idesc, 1u);
-            tc_mma_tf32(d_main, dah, dbh, idesc, first);     // main term
+            for (int ks = 0; ks < BK / 8; ++ks) {
+              const uint64_t dbh = dB_hi + so + (ks ? b_kstep16 : 0u);
+              const uint64_t dbl = dB_lo + so + (ks ? b_kstep16 : 0u);
+              const uint32_t first = (kb == kb0 && ks == 0) ? 0u : 1u;
+              if (g.fuse_n) {
+                // B_lo follows B_hi in the stage: one N = 2*bn MMA yields [hi*hi | hi*lo] in [d_main, d_main + 2*bn)
+                tc_mma_tf32_ts(d_main, ta_hi + 8 * ks, dbh, idesc_ts2, first);
+                tc_mma_tf32_ts(d_small, ta_lo + 8 * ks, dbh, idesc_ts, 1u);
+              } else {
+                tc_mma_tf32_ts(d_small, ta_lo + 8 * ks, dbh, idesc_ts, first);
+                tc_mma_tf32_ts(d_small, ta_hi + 8 * ks, dbl, idesc_ts, 1u);
+                tc_mma_tf32_ts(d_main, ta_hi + 8 * ks, dbh, idesc_ts, first);
+              }
+            }
+            tc_commit(&afree_bar[astage]);                    // frees the TMEM A stage
+          } else {
+#pragma unroll
+            for (int ks = 0; ks < BK / 8; ++ks) {
+              const uint64_t dah = dA_hi + so + (ks ? a_kstep16 : 0u);
+              const uint64_t dal = dA_lo + so + (ks ? a_kstep16 : 0u);
+              const uint64_t dbh = dB_hi + so + (ks ? b_kstep16 : 0u);
+              const uint64_t dbl = dB_lo + so + (ks ? b_kstep16 : 0u);
+              const uint32_t first = (kb == kb0 && ks == 0) ? 0u : 1u;
+              tc_mma_tf32(d_small, dal, dbh, idesc, first);    // cross terms: their own accumulator
+              tc_mma_tf32(d_small, dah, dbl, idesc, 1u);
+              tc_mma_tf32(d_main, dah, dbh, idesc, first);     // main term
+            }
           }
           tc_commit(&empty_bar[stage]);                       // frees the stage when these MMAs retire
           if (kb == kb1 - 1) tc_commit(&tmem_full[acc]);      // accumulators complete
@@ -423,17 +486,101 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        if (++astage == SA) astage = 0;
       }
       if (kb1 <= kb0 && lane == 0) tc_commit(&tmem_full[acc]);  // empty K range: nothing accumulated
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4 && warp < 12) {
     // ======================= converters (warps 4..11) =======================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(80));
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(VER == 2 ? 104 : 80));
     const int ct = threadIdx.x - 128;       // 0..255
     int stage = 0;
     uint32_t phase = 0;
     const int nvec = raw_bytes / 16;
+    if constexpr (VER == 2) {
+      // Two groups of 4 warps take alternate k-blocks.  Thread = one tile row (its warp's TMEM lane quadrant):
+      // 16 raw fp32 of the row -> hi (masked bits) and lo = tf32_rn(x - hi) -> two tcgen05.st.x16 into the TMEM
+      // A ring.  The group's 128 threads also write the B_lo tile (flat float4 pass, layout-agnostic).
+      const int grp = (warp - 4) >> 2;
+      const int q = warp & 3;
+      const int row = q * 32 + lane;
+      const int gt = ct - grp * 128;          // 0..127 inside the group
+      const int nvb = b_bytes / 16;
+      constexpr int MAXVB = ACC_BN * BK * 4 / 16 / 128;   // 3
+      int astage = 0;
+      uint32_t aphase = 0;
+      uint32_t cnt = 0;
+      const uint32_t a_row_off = (uint32_t)row * 64u;
+      const uint32_t a_sw = (uint32_t)(row >> 1) & 3u;     // SWIZZLE_64B: 16-byte chunk index ^= address bits [7:8]
+      for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int split = (int)(tile / tiles_mn);
+        const int64_t kb0 = (int64_t)split * g.kblocks_per_split;
+        const int64_t kb1 = imin<int64_t>(g.kblocks_total, kb0 + g.kblocks_per_split);
+        for (int64_t kb = kb0; kb < kb1; ++kb) {
+          if ((int)(cnt & 1u) == grp) {
+            mbar_wait(&full_bar[stage], phase);
+            if (gt == 0) trace_ev(g.trace, 2, tcount, 2, (unsigned)kb);
+            const unsigned char* st = smem + (size_t)stage * stage_bytes;
+            uint32_t a[16];
+            if (!g.a_mn_major) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const uint4 v = *reinterpret_cast<const uint4*>(st + a_row_off + ((((uint32_t)c) ^ a_sw) << 4));
+                a[4 * c + 0] = v.x; a[4 * c + 1] = v.y; a[4 * c + 2] = v.z; a[4 * c + 3] = v.w;
+              }
+            } else {
+              // MN-major raw tile, unswizzled: 4 blocks of [16 k rows x 32 m]; lanes read consecutive words
+#pragma unroll
+              for (int k = 0; k < 16; ++k)
+                a[k] = *reinterpret_cast<const uint32_t*>(st + q * 2048 + k * 128 + lane * 4);
+            }
+            const float4* braw = reinterpret_cast<const float4*>(st + A_BYTES);
+            float4* blo = reinterpret_cast<float4*>(smem + (size_t)stage * stage_bytes + blo_off);
+            float4 bx[MAXVB];
+#pragma unroll
+            for (int j = 0; j < MAXVB; ++j) {
+              const int i = gt + j * 128;
+              if (i < nvb) bx[j] = braw[i];
+            }
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              hi[k] = a[k] & 0xFFFFE000u;
+              lo[k] = __float_as_uint(tf32_rna_f(__uint_as_float(a[k]) - __uint_as_float(hi[k])));
+            }
+            mbar_wait(&afree_bar[astage], aphase ^ 1);     // MMAs of the k-block that used this A stage are done
+            tc_fence_after();
+            const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(Cfg<VER>::A_COL0 + astage * 32);
+            tc_st16(ta, hi);
+            tc_st16(ta + 16, lo);
+#pragma unroll
+            for (int j = 0; j < MAXVB; ++j) {
+              const int i = gt + j * 128;
+              if (i < nvb) {
+                const float4 x = bx[j];
+                float4 l;
+                l.x = tf32_rna_f(x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u));
+                l.y = tf32_rna_f(x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u));
+                l.z = tf32_rna_f(x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u));
+                l.w = tf32_rna_f(x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u));
+                blo[i] = l;
+              }
+            }
+            if (gt == 0) trace_ev(g.trace, 2, tcount, 8, (unsigned)kb);
+            tc_wait_st();                                                     // TMEM stores complete
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // B_lo visible to the async proxy
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&conv_bar[stage]);
+            if (gt == 0) trace_ev(g.trace, 2, tcount, 3, (unsigned)kb);
+          }
+          ++cnt;
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++astage == SA) { astage = 0; aphase ^= 1; }
+        }
+      }
+    } else
     for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int split = (int)(tile / tiles_mn);
       const int64_t kb0 = (int64_t)split * g.kblocks_per_split;
@@ -532,7 +679,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_wait_relaxed(&tmem_full[acc], acc_phase);
       tc_fence_after();
       if (warp == 0 && lane == 0) trace_ev(g.trace, 3, tcount, 6, (unsigned)tile);
-      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * 2 * MAX_BN);
+      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * 2 * ACC_BN);
       const bool empty_k = ((int64_t)split * g.kblocks_per_split) >= g.kblocks_total;
       for (int c = 0; c < g.bn; c += 32) {
         // operand streams of this chunk are requested first; the TMEM loads + transpose below (~1K clocks)
@@ -549,7 +696,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int half = 0; half < 2; ++half) {
           if (c + 16 * half < g.bn) {
             tc_ld16(t_row + (uint32_t)(c + 16 * half), r);
-            tc_ld16(t_row + (uint32_t)(MAX_BN + c + 16 * half), r2);
+            tc_ld16(t_row + (uint32_t)(cross_off + c + 16 * half), r2);
             tc_wait_ld();
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -639,11 +786,11 @@ bool make_map_3d(CUtensorMap* map, const float* base, int64_t rows, int64_t cols
   return r == CUDA_SUCCESS;
 }
 
-int pick_bn(int64_t N, bool b_mn_major) {
+int pick_bn(int64_t N, bool b_mn_major, int max_bn) {
   const int gran = b_mn_major ? 32 : 16;
-  const int64_t tiles = ceil_div<int64_t>(N, MAX_BN);
+  const int64_t tiles = ceil_div<int64_t>(N, max_bn);
   int64_t bn = ceil_div<int64_t>(ceil_div<int64_t>(N, tiles), gran) * gran;
-  if (bn > MAX_BN) bn = MAX_BN;
+  if (bn > max_bn) bn = max_bn;
   if (bn < gran) bn = gran;
   return (int)bn;
 }
@@ -653,7 +800,7 @@ int pick_bn(int64_t N, bool b_mn_major) {
 long long gemm_tc_launches() { return g_tc_launches.load(); }
 
 int gemm_tc(const float* A, int64_t lda, bool transA, const float* B, int64_t ldb, bool transB, float* C, int64_t ldc,
-            int64_t M, int64_t N, int64_t K, const Epilogue& epi, int split_k, bool accumulate, cudaStream_t stream) {
+            int64_t M, int64_t N, int64_t K, const Epilogue& epi, int split_k, bool accumulate, cudaStream_t stream, int ver) {
   // shapes the tensor-core path does not cover fall back to the exact FFMA engine
   if (M < 64 || N < 16 || K < 16) return KRS_EUNSUPPORTED;
   if (!aligned16(A) || !aligned16(B) || (lda % 4) != 0 || (ldb % 4) != 0) return KRS_EUNSUPPORTED;
@@ -669,7 +816,7 @@ int gemm_tc(const float* A, int64_t lda, bool transA, const float* B, int64_t ld
   g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K;
   g.a_mn_major = transA ? 1 : 0;       // A stored (K,M): M contiguous
   g.b_mn_major = transB ? 0 : 1;       // B stored (K,N): N contiguous ; transB: stored (N,K): K contiguous
-  g.bn = pick_bn(N, g.b_mn_major != 0);
+  g.bn = pick_bn(N, g.b_mn_major != 0, ver == 2 ? Cfg<2>::ACC_BN : Cfg<1>::ACC_BN);
   g.tiles_m = (int)ceil_div<int64_t>(M, BM);
   g.tiles_n = (int)ceil_div<int64_t>(N, g.bn);
   g.kblocks_total = ceil_div<int64_t>(K, BK);
@@ -695,6 +842,11 @@ int gemm_tc(const float* A, int64_t lda, bool transA, const float* B, int64_t ld
   if (const char* e = getenv("KRS_TC_MN_LBO")) g.mn_lbo = atoi(e);       // debug overrides
   if (const char* e = getenv("KRS_TC_MN_SBO")) g.mn_sbo = atoi(e);
   if (const char* e = getenv("KRS_TC_MN_KSTEP")) g.mn_kstep = atoi(e);
+  g.fuse_n = 0;
+  if (const char* e = getenv("KRS_TC_FUSE_N")) g.fuse_n = atoi(e);
+  if (ver != 2 || 2 * g.bn > 256) g.fuse_n = 0;
+  // VER 2: the MN-major A tile is only read by converter threads (consecutive lanes = consecutive words): no swizzle
+  const int a_mn_swz = ver == 2 ? (int)CU_TENSOR_MAP_SWIZZLE_NONE : mn_swz;
 
   CUtensorMap ma, mb;
   bool ok;
@@ -702,9 +854,9 @@ int gemm_tc(const float* A, int64_t lda, bool transA, const float* B, int64_t ld
   const bool allow3d = getenv("KRS_TC_NO_3D") == nullptr;
   if (!g.a_mn_major) ok = make_map(&ma, A, M, K, lda, BK, BM, CU_TENSOR_MAP_SWIZZLE_64B);        // [M][K]
   else {
-    ok = allow3d && make_map_3d(&ma, A, K, M, lda, BM / 32, (CUtensorMapSwizzle)mn_swz);
+    ok = allow3d && make_map_3d(&ma, A, K, M, lda, BM / 32, (CUtensorMapSwizzle)a_mn_swz);
     if (ok) g.a_3d = 1;
-    else ok = make_map(&ma, A, K, M, lda, 32, BK, (CUtensorMapSwizzle)mn_swz);                   // [K][M]
+    else ok = make_map(&ma, A, K, M, lda, 32, BK, (CUtensorMapSwizzle)a_mn_swz);                 // [K][M]
   }
   if (!ok) return KRS_EUNSUPPORTED;
   if (!g.b_mn_major) ok = make_map(&mb, B, N, K, ldb, BK, g.bn, CU_TENSOR_MAP_SWIZZLE_64B);      // [N][K]
@@ -718,7 +870,7 @@ int gemm_tc(const float* A, int64_t lda, bool transA, const float* B, int64_t ld
   if (g.atomic_out && !accumulate)
     KRS_CUDA(cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, stream));
 
-  const size_t stage_bytes = 2 * (size_t)(A_BYTES + g.bn * BK * 4);
+  const size_t stage_bytes = ver == 2 ? (size_t)(A_BYTES + 2 * g.bn * BK * 4) : 2 * (size_t)(A_BYTES + g.bn * BK * 4);
   const size_t budget = 227 * 1024 - 1024 - 512 - EPI_SMEM_BYTES;   // alignment slack + barriers + epilogue staging
   g.stages = (int)imin<int64_t>(MAX_STAGES, (int64_t)(budget / stage_bytes));
   if (g.stages < 3) return KRS_EUNSUPPORTED;
@@ -726,12 +878,15 @@ int gemm_tc(const float* A, int64_t lda, bool transA, const float* B, int64_t ld
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_err = cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   KRS_CUDA(attr_err);
   const int64_t total_tiles = (int64_t)g.tiles_m * g.tiles_n * g.splits;
   const unsigned grid = (unsigned)imax<int64_t>(1, imin<int64_t>(total_tiles, sm_count()));
-  gemm_tc_kernel<<<grid, NUM_THREADS, smem, stream>>>(ma, mb, g);
+  if (ver == 2) gemm_tc_kernel<2><<<grid, NUM_THREADS, smem, stream>>>(ma, mb, g);
+  else gemm_tc_kernel<1><<<grid, NUM_THREADS, smem, stream>>>(ma, mb, g);
   KRS_LAUNCH_CHECK();
   g_tc_launches.fetch_add(1);
   return KRS_OK;

@@ -20,11 +20,11 @@ def _c(t: torch.Tensor) -> torch.Tensor:
 
 def set_gemm_engine(name: str) -> None:
     """'ffma' (exact fp32 FMA products) or 'tcgen05' (tensor pipe, 3xTF32 split)."""
-    check(lib.krs_set_gemm_engine({"ffma": 0, "tcgen05": 1}[name]))
+    check(lib.krs_set_gemm_engine({"ffma": 0, "tcgen05": 1, "tcgen05_ts": 2}[name]))
 
 
 def get_gemm_engine() -> str:
-    return ["ffma", "tcgen05"][lib.krs_get_gemm_engine()]
+    return ["ffma", "tcgen05", "tcgen05_ts"][lib.krs_get_gemm_engine()]
 
 
 # ----------------------------------------------------------------------------- gather

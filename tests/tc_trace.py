@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import keras_rs_b200 as K
 from keras_rs_b200._lib import lib, check, ptr, stream
-K.set_gemm_engine("tcgen05")
+K.set_gemm_engine(os.environ.get("ENGINE", "tcgen05"))
 B, D = 65536, 832
 g = torch.Generator(device="cuda").manual_seed(0)
 x0 = torch.randn((B, D), device="cuda", generator=g); V = torch.randn((D, D), device="cuda", generator=g) * 0.03

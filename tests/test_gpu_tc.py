@@ -1,5 +1,7 @@
 """tcgen05 (3xTF32) GEMM engine vs float64 references and vs the oracle, through the same C ABI.
 Runs last (alphabetical order) so that a fault in the tensor-core kernel cannot mask other results."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -10,10 +12,14 @@ from util import assert_close, dev, npy
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture()
-def tc():
+# engines under test: "tcgen05" (SS operands) and "tcgen05_ts" (A operand in tensor memory)
+ENGINES = [e for e in os.environ.get("KRS_TEST_TC_ENGINES", "tcgen05").split(",") if e]
+
+
+@pytest.fixture(params=ENGINES)
+def tc(request):
     import keras_rs_b200 as K
-    K.set_gemm_engine("tcgen05")
+    K.set_gemm_engine(request.param)
     yield K
     K.set_gemm_engine("ffma")
 
