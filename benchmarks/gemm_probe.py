@@ -56,7 +56,7 @@ def main():
         "dW TN (D,B)x(B,D) split-K": (lambda: K.ops.sgemm(x1, dz, True, False, out=dV), 2.0 * B * D * D, lambda: dV),
         "dx NT (B,D)x(D,D)^T": (lambda: K.ops.sgemm(dz, V, False, True, out=dx), 2.0 * B * D * D, lambda: dx),
         "dense_fwd NN (B,D)x(D,U) bias+relu": (lambda: check(lib.krs_dense_fwd(
-            ptr(x0), ptr(W1), ptr(bias), 1, ptr(yd), B, U, D, s)), 2.0 * B * D * U, lambda: yd),
+            ptr(x0), ptr(W1), ptr(bias), 1, ptr(yd), B, D, U, s)), 2.0 * B * D * U, lambda: yd),
     }
     K.set_gemm_engine("ffma")
     refs = {}

@@ -155,6 +155,31 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
     if (++spins > SPIN_LIMIT) __trap();
   }
 }
+// one lane of a converged warp (elect.sync); the elected branch keeps warp-uniform operands in uniform registers
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred));
+  return pred;
+}
+// mbar_wait for a fully converged warp whose later code must stay provably uniform: the loop exit is a warp vote
+__device__ __forceinline__ void mbar_wait_uniform(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  int spins = 0;
+  while (true) {
+    uint32_t ok = 0;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x400;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (__all_sync(0xffffffffu, ok != 0)) break;
+    if (++spins > SPIN_LIMIT) __trap();
+  }
+}
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
@@ -327,9 +352,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int b_bytes = g.bn * BK * 4;
   const int raw_bytes = A_BYTES + b_bytes;
-  const int stage_bytes = VER == 2 ? raw_bytes + b_bytes : 2 * raw_bytes;   // VER 2: A_raw | B_raw | B_lo
-  const int blo_off = VER == 2 ? raw_bytes : raw_bytes + A_BYTES;             // B_lo tile inside a stage
-  const int cross_off = VER == 2 ? g.bn : ACC_BN;                             // cross-term accumulator = main + cross_off
+  const int stage_bytes = VER == 2 ? raw_bytes + b_bytes : 2 * raw_bytes;   // A_raw | B_raw | B_lo (| A_lo in VER 1)
+  const int blo_off = raw_bytes;               // B_lo directly after B_raw: [B_hi | B_lo] is one 2*bn-row operand (fuse_n)
+  const int alo_off = raw_bytes + b_bytes;     // VER 1 only
+  const int cross_off = g.bn;                  // cross-term accumulator = main + bn columns
   const int STAGES = g.stages;
   float* epi_stage = reinterpret_cast<float*>(smem + (size_t)STAGES * stage_bytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * stage_bytes + EPI_SMEM_BYTES);
@@ -341,7 +367,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + 4);
   uint64_t* afree_bar = bars + 3 * MAX_STAGES + 5;   // [SA] VER 2: MMAs that read the TMEM A stage have completed
 
-  const int warp = threadIdx.x >> 5;
+  // warp index through a shuffle broadcast: ptxas then KNOWS it is warp-uniform, so the role branches are uniform
+  // and descriptors / addresses of the MMA warp live in uniform registers.  With a plain threadIdx.x >> 5 the issue
+  // loop was compiled as a divergent region: every UTCHMMA / UTCBAR got R2UR moves and an ELECT + BRA.U.ANY waterfall
+  // loop and cost ~120-160 clocks to issue, a commit ~200 (benchmarks/umma_probe.cu: 79-107 and ~7 when uniform).
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   int tcount = 0;   // debug trace cursor of this thread's role
 
@@ -366,7 +396,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
   const int64_t tiles_mn = (int64_t)g.tiles_m * g.tiles_n;
   const int64_t total_tiles = tiles_mn * g.splits;
 
@@ -390,27 +420,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int64_t kb0 = (int64_t)split * g.kblocks_per_split;
       const int64_t kb1 = imin<int64_t>(g.kblocks_total, kb0 + g.kblocks_per_split);
       for (int64_t kb = kb0; kb < kb1; ++kb) {
-        // critical path: lane 0 polls without sleeping (a sleeping producer added microseconds per stage
-        // round trip), the other lanes park at the warp barrier
-        if (lane == 0) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], (uint32_t)raw_bytes);
-        }
+        // the whole (converged) warp polls, ONE elected lane arms the transaction count and issues every box of
+        // the stage with warp-uniform coordinates (UTMALDG takes uniform registers: per-lane boxes were compiled
+        // into R2UR + ELECT / BRA.U.ANY waterfall loops)
+        mbar_wait_uniform(&empty_bar[stage], phase ^ 1);
         unsigned char* st = smem + (size_t)stage * stage_bytes;
-        __syncwarp();
         const int k0 = (int)(kb * BK);
-        if (lane < nA) {
+        if (elect_one()) {
+          mbar_expect_tx(&full_bar[stage], (uint32_t)raw_bytes);
           if (!g.a_mn_major) tma_load_2d(st, &tmap_a, k0, tm * BM, &full_bar[stage]);                       // box {16 k, 128 m}
           else if (g.a_3d) tma_load_3d(st, &tmap_a, 0, k0, tm * (BM / 32), &full_bar[stage]);              // box {32 m, 16 k, 4}
-          else tma_load_2d(st + lane * 2048, &tmap_a, tm * BM + lane * 32, k0, &full_bar[stage]);          // box {32 m, 16 k}
-        } else if (lane < nA + nB) {
-          const int blk = lane - nA;
+          else
+            for (int i = 0; i < nA; ++i) tma_load_2d(st + i * 2048, &tmap_a, tm * BM + i * 32, k0, &full_bar[stage]);   // box {32 m, 16 k}
           unsigned char* sb = st + A_BYTES;
           if (!g.b_mn_major) tma_load_2d(sb, &tmap_b, k0, tn * g.bn, &full_bar[stage]);                     // box {16 k, bn n}
           else if (g.b_3d) tma_load_3d(sb, &tmap_b, 0, k0, tn * (g.bn / 32), &full_bar[stage]);            // box {32 n, 16 k, bn/32}
-          else tma_load_2d(sb + blk * 2048, &tmap_b, tn * g.bn + blk * 32, k0, &full_bar[stage]);
+          else
+            for (int i = 0; i < nB; ++i) tma_load_2d(sb + i * 2048, &tmap_b, tn * g.bn + i * 32, k0, &full_bar[stage]);
+          trace_ev(g.trace, 0, tcount, 1, (unsigned)kb);
         }
-        if (lane == 0) trace_ev(g.trace, 0, tcount, 1, (unsigned)kb);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -424,11 +452,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint32_t acc_phase = 0;
     const uint32_t s0 = smem_u32(smem);
     const uint64_t dA_hi = g.a_mn_major ? desc_mnmajor(s0, 0, g) : desc_kmajor(s0, 0);
-    const uint64_t dA_lo = g.a_mn_major ? desc_mnmajor(s0 + raw_bytes, 0, g) : desc_kmajor(s0 + raw_bytes, 0);
+    const uint64_t dA_lo = g.a_mn_major ? desc_mnmajor(s0 + alo_off, 0, g) : desc_kmajor(s0 + alo_off, 0);
     const uint64_t dB_hi = g.b_mn_major ? desc_mnmajor(s0 + A_BYTES, 0, g) : desc_kmajor(s0 + A_BYTES, 0);
     const uint64_t dB_lo = g.b_mn_major ? desc_mnmajor(s0 + blo_off, 0, g) : desc_kmajor(s0 + blo_off, 0);
     const uint32_t idesc_ts = idesc & ~(1u << 15);                                           // TMEM A is K-major
     const uint32_t idesc_ts2 = (idesc_ts & ~(0x3Fu << 17)) | ((uint32_t)((2 * g.bn) >> 3) << 17);   // N = 2*bn
+    const uint32_t idesc2 = (idesc & ~(0x3Fu << 17)) | ((uint32_t)((2 * g.bn) >> 3) << 17);
     int astage = 0;
     const uint32_t a_kstep16 = (uint32_t)(g.a_mn_major ? g.mn_kstep : 32) >> 4;
     const uint32_t b_kstep16 = (uint32_t)(g.b_mn_major ? g.mn_kstep : 32) >> 4;
@@ -437,13 +466,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int64_t kb0 = (int64_t)split * g.kblocks_per_split;
       const int64_t kb1 = imin<int64_t>(g.kblocks_total, kb0 + g.kblocks_per_split);
       mbar_wait_relaxed(&tmem_empty[acc], acc_phase ^ 1);
+      __syncwarp();
       tc_fence_after();
       const uint32_t d_main = tmem_base + (uint32_t)(acc * 2 * ACC_BN);
       const uint32_t d_small = d_main + (uint32_t)cross_off;
       for (int64_t kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(&conv_bar[stage], phase);
+        mbar_wait_uniform(&conv_bar[stage], phase);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           trace_ev(g.trace, 1, tcount, 4, (unsigned)kb);
           // descriptors = per-launch base (stage 0, k-step 0) + (stage offset + k-step offset) >> 4 in the
           // 14-bit start-address field: one 32-bit add each instead of rebuilding the bit fields
@@ -475,9 +505,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               const uint64_t dbh = dB_hi + so + (ks ? b_kstep16 : 0u);
               const uint64_t dbl = dB_lo + so + (ks ? b_kstep16 : 0u);
               const uint32_t first = (kb == kb0 && ks == 0) ? 0u : 1u;
-              tc_mma_tf32(d_small, dal, dbh, idesc, first);    // cross terms: their own accumulator
-              tc_mma_tf32(d_small, dah, dbl, idesc, 1u);
-              tc_mma_tf32(d_main, dah, dbh, idesc, first);     // main term
+              if (g.fuse_n) {
+                tc_mma_tf32(d_main, dah, dbh, idesc2, first);    // [hi*hi | hi*lo] -> [main | cross], N = 2*bn
+                tc_mma_tf32(d_small, dal, dbh, idesc, 1u);       // lo*hi -> cross
+              } else {
+                tc_mma_tf32(d_small, dal, dbh, idesc, first);    // cross terms: their own accumulator
+                tc_mma_tf32(d_small, dah, dbl, idesc, 1u);
+                tc_mma_tf32(d_main, dah, dbh, idesc, first);     // main term
+              }
             }
           }
           tc_commit(&empty_bar[stage]);                       // frees the stage when these MMAs retire
@@ -488,7 +523,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
         if (++astage == SA) astage = 0;
       }
-      if (kb1 <= kb0 && lane == 0) tc_commit(&tmem_full[acc]);  // empty K range: nothing accumulated
+      if (kb1 <= kb0 && elect_one()) tc_commit(&tmem_full[acc]);  // empty K range: nothing accumulated
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4 && warp < 12) {
@@ -520,7 +555,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int64_t kb = kb0; kb < kb1; ++kb) {
           if ((int)(cnt & 1u) == grp) {
             mbar_wait(&full_bar[stage], phase);
-            if (gt == 0) trace_ev(g.trace, 2, tcount, 2, (unsigned)kb);
+            if (ct == 0) trace_ev(g.trace, 2, tcount, 2, (unsigned)kb);
             const unsigned char* st = smem + (size_t)stage * stage_bytes;
             uint32_t a[16];
             if (!g.a_mn_major) {
@@ -551,6 +586,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
             mbar_wait(&afree_bar[astage], aphase ^ 1);     // MMAs of the k-block that used this A stage are done
             tc_fence_after();
+            if (ct == 0) trace_ev(g.trace, 2, tcount, 9, (unsigned)kb);
             const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(Cfg<VER>::A_COL0 + astage * 32);
             tc_st16(ta, hi);
             tc_st16(ta + 16, lo);
@@ -567,13 +603,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 blo[i] = l;
               }
             }
-            if (gt == 0) trace_ev(g.trace, 2, tcount, 8, (unsigned)kb);
+            if (ct == 0) trace_ev(g.trace, 2, tcount, 8, (unsigned)kb);
             tc_wait_st();                                                     // TMEM stores complete
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // B_lo visible to the async proxy
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&conv_bar[stage]);
-            if (gt == 0) trace_ev(g.trace, 2, tcount, 3, (unsigned)kb);
+            if (ct == 0) trace_ev(g.trace, 2, tcount, 3, (unsigned)kb);
           }
           ++cnt;
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -590,6 +626,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (ct == 0) trace_ev(g.trace, 2, tcount, 2, (unsigned)kb);
         float4* raw = reinterpret_cast<float4*>(smem + (size_t)stage * stage_bytes);
         float4* lo = reinterpret_cast<float4*>(smem + (size_t)stage * stage_bytes + raw_bytes);
+        constexpr int A_VECS = A_BYTES / 16;
+        const int b_vecs = b_bytes / 16;
         // all loads first (<= 6 float4 per thread at bn = 256), then split + store: one shared-memory
         // latency per k-block instead of one per element
         constexpr int MAXV = (A_BYTES + MAX_BN * BK * 4) / 16 / NUM_CONV_THREADS;   // 6
@@ -614,7 +652,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             l.z = tf32_rna_f(x.z - h.z);
             l.w = tf32_rna_f(x.w - h.w);
             if (!g.no_mask) raw[i] = h;
-            lo[i] = l;
+            lo[i < A_VECS ? i + b_vecs : i - A_VECS] = l;      // lo region = B_lo | A_lo
           }
         }
         if (ct == 0) trace_ev(g.trace, 2, tcount, 8, (unsigned)kb);
@@ -725,6 +763,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 if (nq + j < g.N) epilogue_scalar(g, m, nq + j, vv[j]);
             }
           }
+          if (i == 0 && warp == 0 && lane == 0) trace_ev(g.trace, 3, tcount, 13, (unsigned)c);
+          if (i == 3 && warp == 0 && lane == 0) trace_ev(g.trace, 3, tcount, 14, (unsigned)c);
         }
         __syncwarp();                        // staging tile is rewritten by the next chunk
         if (warp == 0 && lane == 0) trace_ev(g.trace, 3, tcount, 12, (unsigned)c);
@@ -844,7 +884,7 @@ int gemm_tc(const float* A, int64_t lda, bool transA, const float* B, int64_t ld
   if (const char* e = getenv("KRS_TC_MN_KSTEP")) g.mn_kstep = atoi(e);
   g.fuse_n = 0;
   if (const char* e = getenv("KRS_TC_FUSE_N")) g.fuse_n = atoi(e);
-  if (ver != 2 || 2 * g.bn > 256) g.fuse_n = 0;
+  if (2 * g.bn > 256) g.fuse_n = 0;
   // VER 2: the MN-major A tile is only read by converter threads (consecutive lanes = consecutive words): no swizzle
   const int a_mn_swz = ver == 2 ? (int)CU_TENSOR_MAP_SWIZZLE_NONE : mn_swz;
 

@@ -1,10 +1,12 @@
-"""Debug harness: per-role clock64 timeline of CTA 0 of one tcgen05 GEMM (cross forward, C2 shape)."""
+"""Debug harness: per-role clock64 timeline of CTA 0 of one tcgen05 GEMM (cross forward, C2 shape).
+ENGINE=tcgen05|tcgen05_ts  MODE=cross|cross_noh2|cross_x1|dense|sgemm"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import keras_rs_b200 as K
 from keras_rs_b200._lib import lib, check, ptr, stream
-K.set_gemm_engine(os.environ.get("ENGINE", "tcgen05"))
+ENGINE = os.environ.get("ENGINE", "tcgen05")
+K.set_gemm_engine(ENGINE)
 B, D = 65536, 832
 g = torch.Generator(device="cuda").manual_seed(0)
 x0 = torch.randn((B, D), device="cuda", generator=g); V = torch.randn((D, D), device="cuda", generator=g) * 0.03
@@ -24,6 +26,9 @@ def run():
         K.ops.sgemm(x0, V, out=y)
 for _ in range(2): run()
 torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(); run(); e1.record(); torch.cuda.synchronize()
+print("ENGINE", ENGINE, "MODE", MODE, "FUSE_N", os.environ.get("KRS_TC_FUSE_N", "0"), "kernel ms", round(e0.elapsed_time(e1), 4))
 tr = torch.zeros(16001 + 16, dtype=torch.int64, device="cuda")
 lib.krs_gemm_tc_set_trace(tr.data_ptr())
 run(); torch.cuda.synchronize()
@@ -34,31 +39,42 @@ for role in range(4):
     for i in range(2000):
         a, c = int(t[1 + role * 4000 + 2 * i]), int(t[2 + role * 4000 + 2 * i])
         if c: ev.append((a >> 32, a & 0xffffffff, c))
-n = len(ev)
 ev.sort(key=lambda e: e[2]); t0 = ev[0][2]
-names = {8: "conv stores issued", 9: "conv fence done", 1: "TMA issued", 2: "conv saw full", 3: "conv done", 4: "mma saw conv", 5: "mma committed", 6: "epi start", 7: "epi done"}
-print("MODE", MODE, "entries", n)
+names = {1: "TMA issued", 2: "conv saw full", 9: "conv fence done / (ts) A stage free", 8: "conv stores issued", 3: "conv done",
+         4: "mma saw conv", 5: "mma committed", 6: "epi start", 7: "epi done"}
+print("entries", len(ev))
 by = {k: [(i, c - t0) for tag, i, c in ev if tag == k] for k in names}
 for k in (6, 7):
     print(names[k], by[k][:6])
-# per k-block deltas for the first tile (52 k-blocks) and the second
+KB = 52   # k-blocks per tile at K = 832
+def per_tile(tag, tile):
+    """{kb: clock} of this tag's events inside the tile-th visit (events are in time order; kb restarts at 0 per tile)."""
+    out, seen_tile, prev = {}, -1, 10 ** 9
+    for i, c in by[tag]:
+        if i < prev: seen_tile += 1
+        prev = i
+        if seen_tile == tile: out[i] = c
+    return out
+def med(a, b2, keys=None):
+    keys = sorted(set(a) & set(b2)) if keys is None else keys
+    d = [b2[k] - a[k] for k in keys if k in a and k in b2]
+    return float(np.median(d)) if d else float("nan")
 for tile in (0, 1, 2):
-    lo, hi = tile * 52, tile * 52 + 52
-    def seq(k): return [c for (i, c) in by[k][lo:hi]]
-    s1, s2, s3, s4, s5 = seq(1), seq(2), seq(3), seq(4), seq(5)
-    s8, s9 = seq(8), seq(9)
-    if len(s8) == 52:
-        print(f"   conv breakdown: full->stores issued {np.median(np.array(s8)-np.array(s2)):.0f}; stores->fence done {np.median(np.array(s9)-np.array(s8)):.0f}; fence->arrive {np.median(np.array(s3)-np.array(s9)):.0f}")
-    if len(s5) < 52: break
-    d = lambda a: np.diff(np.array(a))
-    print(f"tile {tile}: mainloop {s5[-1]-s4[0]} clks; per-kb period mma-committed median {np.median(d(s5)):.0f}; TMA-issue period {np.median(d(s1)):.0f}; "
-          f"TMA issue->full seen median {np.median(np.array(s2)-np.array(s1)):.0f}; conv time median {np.median(np.array(s3)-np.array(s2)):.0f}; "
-          f"conv done->mma saw {np.median(np.array(s4)-np.array(s3)):.0f}; mma issue {np.median(np.array(s5)-np.array(s4)):.0f}")
-    print("   first 8 kb: TMA", [c - s1[0] for c in s1[:8]], " full", [c - s1[0] for c in s2[:8]], " convdone", [c - s1[0] for c in s3[:8]], " commit", [c - s1[0] for c in s5[:8]])
-
-# epilogue chunk breakdown (first tile)
+    T = {k: per_tile(k, tile) for k in (1, 2, 9, 8, 3, 4, 5)}
+    if len(T[5]) < KB: break
+    c5 = [T[5][k] for k in sorted(T[5])]
+    print(f"tile {tile}: mainloop {c5[-1] - T[4][0]} clks; k-block period (mma committed) median {np.median(np.diff(c5)):.0f}; "
+          f"TMA issue->conv saw full {med(T[1], T[2]):.0f}; conv: full->(9) {med(T[2], T[9]):.0f}, (9)->stores issued {med(T[9], T[8]):.0f}, "
+          f"full->stores issued {med(T[2], T[8]):.0f}, stores->done {med(T[8], T[3]):.0f}, full->done {med(T[2], T[3]):.0f}; "
+          f"conv done->mma saw {med(T[3], T[4]):.0f}; mma saw->committed {med(T[4], T[5]):.0f}")
+    ks = sorted(T[2])[:8]
+    print("   traced conv k-blocks", ks, " TMA", [T[1].get(k) for k in ks], " full", [T[2].get(k) for k in ks], " convdone", [T[3].get(k) for k in ks],
+          " mma saw", [T[4].get(k) for k in ks], " commit", [T[5].get(k) for k in ks])
 e10 = [c for tag, i, c in ev if tag == 10][:8]; e11 = [c for tag, i, c in ev if tag == 11][:8]; e12 = [c for tag, i, c in ev if tag == 12][:8]
-if len(e12) >= 4:
+e13 = [c for tag, i, c in ev if tag == 13][:8]; e14 = [c for tag, i, c in ev if tag == 14][:8]
+if len(e13) >= 3:
+    print("epilogue chunks (tile 0): loaded->row group 0 done", [b - a for a, b in zip(e11, e13)], " group 0->3", [b - a for a, b in zip(e13, e14)], " group 3->7 (+syncwarp)", [b - a for a, b in zip(e14, e12)])
+if len(e12) >= 3:
     print("epilogue chunks (tile 0): begin->tmem loaded", [b - a for a, b in zip(e10, e11)])
     print("                          loaded->chunk done ", [b - a for a, b in zip(e11, e12)])
-    print("                          chunk period       ", list(np.diff(np.array(e10))))
+    print("                          chunk period       ", [int(x) for x in np.diff(np.array(e10))])
