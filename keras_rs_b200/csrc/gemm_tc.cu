@@ -275,35 +275,55 @@ __device__ __forceinline__ const float* epi_stream1(const Epilogue& e) {
 __device__ __forceinline__ const float* epi_stream2(const Epilogue& e) {
   return e.kind == EPI_CROSS ? e.x : (e.kind == EPI_ADD2 ? e.add2 : nullptr);
 }
-// vec path: n..n+3 in range, all pointers 16-byte aligned
-__device__ __forceinline__ void epilogue_f4(const TcArgs& g, int64_t m, int64_t n, float4 acc, float4 s1, float4 s2, float4 bv) {
-  const Epilogue& e = g.epi;
-  const int64_t o = m * g.ldc + n;
-  if (g.atomic_out) {
-    atomicAdd(reinterpret_cast<float4*>(g.C + o), acc);          // RED.E.ADD.F32x4, round-to-nearest in L2
+// Compile-time epilogue kinds: the kernel is instantiated per (kind, activation class) so that the per-float4 code
+// is straight-line.  The first version dispatched on g.epi.kind / act / atomic_out / accumulate at run time inside the
+// innermost loop: ~10 LDCU -> UISETP -> BRA.U chains plus a jump table per ELEMENT for the activation cost ~1250 clocks
+// per 4-row group and made the epilogue as long as the mainloop (tests/tc_trace.py tags 13/14).
+enum TcKind { TK_STORE = 0, TK_ACCUM = 1, TK_ATOMIC = 2, TK_BIAS_ACT = 3, TK_CROSS = 4, TK_ADD2 = 5, TK_COUNT = 6 };
+enum TcAct { TA_LINEAR = 0, TA_RELU = 1, TA_GENERIC = 2, TA_COUNT = 3 };
+template <int ACT>
+__device__ __forceinline__ float tc_act(int act, float z) {
+  if (ACT == TA_LINEAR) return z;
+  if (ACT == TA_RELU) return fmaxf(z, 0.f);
+  return act_apply(act, z);
+}
+// Run-time epilogue operands copied to registers once per kernel (warp-uniform values).
+struct EpiRegs {
+  float* C;
+  float* h2_out;
+  float* z_out;
+  int64_t ldc;
+  float diag, alpha1, alpha2;
+  int act;
+  bool has1, has2;
+};
+// vec path: n..n+3 in range, all pointers 16-byte aligned; o = m * ldc + n
+template <int KIND, int ACT>
+__device__ __forceinline__ void epilogue_f4(const EpiRegs& e, int64_t o, float4 acc, float4 s1, float4 s2, float4 bv) {
+  if (KIND == TK_ATOMIC) {
+    atomicAdd(reinterpret_cast<float4*>(e.C + o), acc);          // RED.E.ADD.F32x4, round-to-nearest in L2
     return;
   }
-  float v[4] = {acc.x, acc.y, acc.z, acc.w};
+  const float v[4] = {acc.x, acc.y, acc.z, acc.w};
   const float a1[4] = {s1.x, s1.y, s1.z, s1.w};
   const float a2[4] = {s2.x, s2.y, s2.z, s2.w};
   const float b[4] = {bv.x, bv.y, bv.z, bv.w};
-  float out[4], h2v[4], zv[4];
-  if (e.kind == EPI_NONE) {
-    if (g.accumulate) {
-      const float4 c = *reinterpret_cast<const float4*>(g.C + o);
-      out[0] = v[0] + c.x; out[1] = v[1] + c.y; out[2] = v[2] + c.z; out[3] = v[3] + c.w;
-    } else {
+  float out[4];
+  if (KIND == TK_STORE) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) out[j] = v[j];
-    }
-  } else if (e.kind == EPI_BIAS_ACT) {
+    for (int j = 0; j < 4; ++j) out[j] = v[j];
+  } else if (KIND == TK_ACCUM) {
+    const float4 c = *reinterpret_cast<const float4*>(e.C + o);
+    out[0] = v[0] + c.x; out[1] = v[1] + c.y; out[2] = v[2] + c.z; out[3] = v[3] + c.w;
+  } else if (KIND == TK_BIAS_ACT) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) out[j] = act_apply(e.act, v[j] + b[j]);
-  } else if (e.kind == EPI_CROSS) {
+    for (int j = 0; j < 4; ++j) out[j] = tc_act<ACT>(e.act, v[j] + b[j]);
+  } else if (KIND == TK_CROSS) {
+    float h2v[4], zv[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float z = v[j] + b[j];
-      const float a = act_apply(e.act, z);
+      const float a = tc_act<ACT>(e.act, z);
       const float h2 = (e.diag != 0.f) ? a + e.diag * a2[j] : a;     // feature_cross.py:191-192
       zv[j] = z;
       h2v[j] = h2;
@@ -311,36 +331,35 @@ __device__ __forceinline__ void epilogue_f4(const TcArgs& g, int64_t m, int64_t 
     }
     if (e.h2_out) *reinterpret_cast<float4*>(e.h2_out + o) = make_float4(h2v[0], h2v[1], h2v[2], h2v[3]);
     if (e.z_out) *reinterpret_cast<float4*>(e.z_out + o) = make_float4(zv[0], zv[1], zv[2], zv[3]);
-  } else {  // EPI_ADD2
+  } else {  // TK_ADD2
 #pragma unroll
-    for (int j = 0; j < 4; ++j) out[j] = v[j] + (e.add1 ? e.alpha1 * a1[j] : 0.f) + (e.add2 ? e.alpha2 * a2[j] : 0.f);
+    for (int j = 0; j < 4; ++j) out[j] = v[j] + (e.has1 ? e.alpha1 * a1[j] : 0.f) + (e.has2 ? e.alpha2 * a2[j] : 0.f);
   }
-  *reinterpret_cast<float4*>(g.C + o) = make_float4(out[0], out[1], out[2], out[3]);
+  *reinterpret_cast<float4*>(e.C + o) = make_float4(out[0], out[1], out[2], out[3]);
 }
-// scalar path for ragged / unaligned outputs
-__device__ __forceinline__ void epilogue_scalar(const TcArgs& g, int64_t m, int64_t n, float acc) {
-  const Epilogue& e = g.epi;
-  const int64_t o = m * g.ldc + n;
-  if (g.atomic_out) { atomicAdd(g.C + o, acc); return; }
-  const float* p1 = epi_stream1(e);
-  const float* p2 = epi_stream2(e);
-  const float s1 = p1 ? p1[o] : 0.f, s2 = p2 ? p2[o] : 0.f, b = e.bias ? e.bias[n] : 0.f;
+// scalar path for ragged / unaligned outputs (p1 / p2: the two operand streams, bias nullable)
+template <int KIND, int ACT>
+__device__ __forceinline__ void epilogue_scalar(const EpiRegs& e, const float* p1, const float* p2, const float* bias,
+                                                int64_t o, int64_t n, float acc) {
+  if (KIND == TK_ATOMIC) { atomicAdd(e.C + o, acc); return; }
+  const float s1 = p1 ? p1[o] : 0.f, s2 = p2 ? p2[o] : 0.f, b = bias ? bias[n] : 0.f;
   float out;
-  if (e.kind == EPI_NONE) out = acc + (g.accumulate ? g.C[o] : 0.f);
-  else if (e.kind == EPI_BIAS_ACT) out = act_apply(e.act, acc + b);
-  else if (e.kind == EPI_CROSS) {
+  if (KIND == TK_STORE) out = acc;
+  else if (KIND == TK_ACCUM) out = acc + e.C[o];
+  else if (KIND == TK_BIAS_ACT) out = tc_act<ACT>(e.act, acc + b);
+  else if (KIND == TK_CROSS) {
     const float z = acc + b;
-    const float a = act_apply(e.act, z);
+    const float a = tc_act<ACT>(e.act, z);
     const float h2 = (e.diag != 0.f) ? a + e.diag * s2 : a;
     if (e.h2_out) e.h2_out[o] = h2;
     if (e.z_out) e.z_out[o] = z;
     out = s1 * h2 + s2;
   } else out = acc + (p1 ? e.alpha1 * s1 : 0.f) + (p2 ? e.alpha2 * s2 : 0.f);
-  g.C[o] = out;
+  e.C[o] = out;
 }
 
 // ---------------------------------------------------------------- the kernel
-template <int VER>
+template <int VER, int KIND, int ACT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const TcArgs g) {
   constexpr int ACC_BN = Cfg<VER>::ACC_BN;
@@ -671,8 +690,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int quad = warp & 3;              // TMEM lane quadrant this warp may read
     float* T = epi_stage + warp * (32 * EPI_LD);           // this warp's 32 x 32 staging tile
     const int rr = lane >> 3, c4 = lane & 7;               // coalesced domain: 4 rows x 8 float4 per instruction
-    const float* p1 = epi_stream1(g.epi);
-    const float* p2 = epi_stream2(g.epi);
+    const float* p1 = (KIND == TK_CROSS || KIND == TK_ADD2) ? epi_stream1(g.epi) : nullptr;
+    const float* p2 = (KIND == TK_CROSS || KIND == TK_ADD2) ? epi_stream2(g.epi) : nullptr;
+    const float* bias = (KIND == TK_CROSS || KIND == TK_BIAS_ACT) ? g.epi.bias : nullptr;
+    EpiRegs er;
+    er.C = g.C; er.h2_out = g.epi.h2_out; er.z_out = g.epi.z_out; er.ldc = g.ldc;
+    er.diag = g.epi.diag; er.alpha1 = g.epi.alpha1; er.alpha2 = g.epi.alpha2; er.act = g.epi.act;
+    er.has1 = p1 != nullptr; er.has2 = p2 != nullptr;
     // L2 prefetch of the epilogue operand tiles (x0 / x, add1 / add2) of a FUTURE tile: issued one tile ahead so the
     // epilogue's loads hit L2 instead of paying DRAM latency with only 4 warps' worth of requests in flight
     auto prefetch_tile_l2 = [&](int64_t t) {
@@ -726,7 +750,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int64_t nq = nbase + c + c4 * 4;
         const bool vec_ok = g.epi_vec && (c + c4 * 4 < g.bn) && (nq + 3 < g.N);
         float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (vec_ok && g.epi.bias) bv = __ldg(reinterpret_cast<const float4*>(g.epi.bias + nq));
+        if (vec_ok && bias) bv = __ldg(reinterpret_cast<const float4*>(bias + nq));
         if (warp == 0 && lane == 0) trace_ev(g.trace, 3, tcount, 10, (unsigned)c);
         // TMEM -> registers (this lane = one row), main + cross-term accumulators, fp32 RN add
         uint32_t r[16], r2[16];
@@ -755,12 +779,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const int64_t m = m_base + row;
           if (m < g.M && (c + c4 * 4 < g.bn)) {
             const float4 v = *reinterpret_cast<const float4*>(T + row * EPI_LD + c4 * 4);
+            const int64_t o = m * er.ldc + nq;
             if (vec_ok) {
-              epilogue_f4(g, m, nq, v, a1[i], a2[i], bv);
+              epilogue_f4<KIND, ACT>(er, o, v, a1[i], a2[i], bv);
             } else {
               const float vv[4] = {v.x, v.y, v.z, v.w};
               for (int j = 0; j < 4; ++j)
-                if (nq + j < g.N) epilogue_scalar(g, m, nq + j, vv[j]);
+                if (nq + j < g.N) epilogue_scalar<KIND, ACT>(er, p1, p2, bias, o + j, nq + j, vv[j]);
             }
           }
           if (i == 0 && warp == 0 && lane == 0) trace_ev(g.trace, 3, tcount, 13, (unsigned)c);
@@ -824,6 +849,30 @@ bool make_map_3d(CUtensorMap* map, const float* base, int64_t rows, int64_t cols
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
+}
+
+using TcKernel = void (*)(const CUtensorMap, const CUtensorMap, const TcArgs);
+template <int VER>
+TcKernel kernel_table_v(int kind, int act) {
+  switch (kind) {
+    case TK_STORE: return gemm_tc_kernel<VER, TK_STORE, TA_LINEAR>;
+    case TK_ACCUM: return gemm_tc_kernel<VER, TK_ACCUM, TA_LINEAR>;
+    case TK_ATOMIC: return gemm_tc_kernel<VER, TK_ATOMIC, TA_LINEAR>;
+    case TK_ADD2: return gemm_tc_kernel<VER, TK_ADD2, TA_LINEAR>;
+    case TK_BIAS_ACT:
+      return act == TA_LINEAR ? gemm_tc_kernel<VER, TK_BIAS_ACT, TA_LINEAR>
+                              : (act == TA_RELU ? gemm_tc_kernel<VER, TK_BIAS_ACT, TA_RELU> : gemm_tc_kernel<VER, TK_BIAS_ACT, TA_GENERIC>);
+    case TK_CROSS:
+      return act == TA_LINEAR ? gemm_tc_kernel<VER, TK_CROSS, TA_LINEAR>
+                              : (act == TA_RELU ? gemm_tc_kernel<VER, TK_CROSS, TA_RELU> : gemm_tc_kernel<VER, TK_CROSS, TA_GENERIC>);
+  }
+  return nullptr;
+}
+// nullptr for (kind, act) pairs that are never launched (activation classes of kinds without an activation)
+TcKernel kernel_table(int ver, int kind, int act) {
+  const bool has_act = kind == TK_BIAS_ACT || kind == TK_CROSS;
+  if (!has_act && act != TA_LINEAR) return nullptr;
+  return ver == 2 ? kernel_table_v<2>(kind, act) : kernel_table_v<1>(kind, act);
 }
 
 int pick_bn(int64_t N, bool b_mn_major, int max_bn) {
@@ -918,15 +967,27 @@ int gemm_tc(const float* A, int64_t lda, bool transA, const float* B, int64_t ld
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    for (int v = 0; v < 2 && attr_err == cudaSuccess; ++v)
+      for (int k = 0; k < TK_COUNT && attr_err == cudaSuccess; ++k)
+        for (int a = 0; a < TA_COUNT && attr_err == cudaSuccess; ++a)
+          if (kernel_table(v + 1, k, a))
+            attr_err = cudaFuncSetAttribute(kernel_table(v + 1, k, a), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   KRS_CUDA(attr_err);
   const int64_t total_tiles = (int64_t)g.tiles_m * g.tiles_n * g.splits;
   const unsigned grid = (unsigned)imax<int64_t>(1, imin<int64_t>(total_tiles, sm_count()));
-  if (ver == 2) gemm_tc_kernel<2><<<grid, NUM_THREADS, smem, stream>>>(ma, mb, g);
-  else gemm_tc_kernel<1><<<grid, NUM_THREADS, smem, stream>>>(ma, mb, g);
+  int kind;
+  switch (epi.kind) {
+    case EPI_NONE: kind = g.atomic_out ? TK_ATOMIC : (g.accumulate ? TK_ACCUM : TK_STORE); break;
+    case EPI_BIAS_ACT: kind = TK_BIAS_ACT; break;
+    case EPI_CROSS: kind = TK_CROSS; break;
+    default: kind = TK_ADD2; break;
+  }
+  const bool has_act = kind == TK_BIAS_ACT || kind == TK_CROSS;
+  const int actc = !has_act ? TA_LINEAR : (epi.act == KRS_ACT_LINEAR ? TA_LINEAR : (epi.act == KRS_ACT_RELU ? TA_RELU : TA_GENERIC));
+  TcKernel kfn = kernel_table(ver == 2 ? 2 : 1, kind, actc);
+  KRS_REQUIRE(kfn != nullptr, "gemm_tc: no kernel for kind %d act %d", kind, actc);
+  kfn<<<grid, NUM_THREADS, smem, stream>>>(ma, mb, g);
   KRS_LAUNCH_CHECK();
   g_tc_launches.fetch_add(1);
   return KRS_OK;
