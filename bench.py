@@ -144,7 +144,7 @@ def run_ours(a):
 
     engine = a.engine
     if engine == "auto":
-        engine = os.environ.get("KRS_GEMM_ENGINE", "tcgen05")   # tensor-pipe 3xTF32 (fp32-level accuracy); "ffma" = exact fp32 FMA
+        engine = os.environ.get("KRS_GEMM_ENGINE", "tcgen05_ts")   # tensor-pipe 3xTF32 (fp32-level accuracy); "ffma" = exact fp32 FMA
     K.set_gemm_engine(engine)
 
     B, F, V, E, L = a.batch, a.features, a.vocab, a.embed_dim, a.cross_layers

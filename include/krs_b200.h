@@ -48,6 +48,11 @@ long long krs_gemm_tc_launch_count(void);
 /* Debug: device buffer of >= 16001 uint64 receiving a per-role clock64 timeline of CTA 0 of subsequent
  * tcgen05 GEMM launches ([0] = entry count, then (tag<<32|index, clock) pairs); NULL disables. */
 int krs_gemm_tc_set_trace(void* dev_buf);
+/* Optional caller-owned device scratch (16-byte aligned) for the tcgen05 engines: when a GEMM's B operand is a small
+ * matrix re-read by many row tiles (the weights of FeatureCross / Dense), its low-order TF32 plane is computed once
+ * per call into this buffer and streamed by TMA instead of being re-derived per tile.  NULL / 0 unregisters.  The
+ * buffer must outlive every GEMM call, and calls that use it must be issued on one stream at a time. */
+int krs_gemm_set_workspace(void* dev_buf, size_t bytes);
 
 /* ------------------------------------------------------------------ activations
  * keras.activations used as FeatureCross.pre_activation / Dense.activation

@@ -11,9 +11,10 @@ from .ops import get_gemm_engine, set_gemm_engine  # noqa: F401
 
 import os as _os
 
-# dense contractions: tensor pipe (tcgen05, 3xTF32 split, fp32-level accuracy) unless KRS_GEMM_ENGINE=ffma asks
-# for the exact-fp32 FMA engine.  Shapes the tensor-core kernel does not take fall through to FFMA automatically.
-set_gemm_engine(_os.environ.get("KRS_GEMM_ENGINE", "tcgen05"))
+# dense contractions: tensor pipe (tcgen05, 3xTF32 split, fp32-level accuracy; "tcgen05_ts" keeps the A operand in
+# tensor memory, "tcgen05" reads both operands from shared memory) unless KRS_GEMM_ENGINE=ffma asks for the exact-fp32
+# FMA engine.  Shapes the tensor-core kernel does not take fall through to FFMA automatically.
+set_gemm_engine(_os.environ.get("KRS_GEMM_ENGINE", "tcgen05_ts"))
 
 __version__ = "0.1.0"
 

@@ -87,7 +87,8 @@ struct TcArgs {
   int epi_vec;            // rows of C / h2 / z / aux streams are 16-byte aligned (vector epilogue)
   int no_mask;            // 1: leave hi = raw fp32 bits (hardware ignores the low 13 mantissa bits)
   int mn_lbo, mn_sbo, mn_kstep, mn_layout;   // MN-major descriptor strides (bytes) and UMMA layout type
-  int fuse_n;             // VER 2: one N = 2*bn MMA computes A_hi x [B_hi | B_lo] (main and hi*lo terms together)
+  int fuse_n;             // one N = 2*bn MMA computes A_hi x [B_hi | B_lo] (main and hi*lo terms together)
+  int b_lo_tma;           // B_lo comes precomputed from global memory by TMA (tmap_blo); converters skip the B tile
   Epilogue epi;
 };
 
@@ -361,7 +362,8 @@ __device__ __forceinline__ void epilogue_scalar(const EpiRegs& e, const float* p
 // ---------------------------------------------------------------- the kernel
 template <int VER, int KIND, int ACT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const TcArgs g) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const __grid_constant__ CUtensorMap tmap_blo, const TcArgs g) {
   constexpr int ACC_BN = Cfg<VER>::ACC_BN;
   constexpr int SA = Cfg<VER>::SA;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -446,7 +448,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         unsigned char* st = smem + (size_t)stage * stage_bytes;
         const int k0 = (int)(kb * BK);
         if (elect_one()) {
-          mbar_expect_tx(&full_bar[stage], (uint32_t)raw_bytes);
+          mbar_expect_tx(&full_bar[stage], (uint32_t)(raw_bytes + (g.b_lo_tma ? b_bytes : 0)));
           if (!g.a_mn_major) tma_load_2d(st, &tmap_a, k0, tm * BM, &full_bar[stage]);                       // box {16 k, 128 m}
           else if (g.a_3d) tma_load_3d(st, &tmap_a, 0, k0, tm * (BM / 32), &full_bar[stage]);              // box {32 m, 16 k, 4}
           else
@@ -456,6 +458,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           else if (g.b_3d) tma_load_3d(sb, &tmap_b, 0, k0, tn * (g.bn / 32), &full_bar[stage]);            // box {32 n, 16 k, bn/32}
           else
             for (int i = 0; i < nB; ++i) tma_load_2d(sb + i * 2048, &tmap_b, tn * g.bn + i * 32, k0, &full_bar[stage]);
+          if (g.b_lo_tma) {       // same boxes from the precomputed lo plane, landing right behind B_raw
+            unsigned char* sl = st + blo_off;
+            if (!g.b_mn_major) tma_load_2d(sl, &tmap_blo, k0, tn * g.bn, &full_bar[stage]);
+            else if (g.b_3d) tma_load_3d(sl, &tmap_blo, 0, k0, tn * (g.bn / 32), &full_bar[stage]);
+            else
+              for (int i = 0; i < nB; ++i) tma_load_2d(sl + i * 2048, &tmap_blo, tn * g.bn + i * 32, k0, &full_bar[stage]);
+          }
           trace_ev(g.trace, 0, tcount, 1, (unsigned)kb);
         }
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -490,7 +499,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const uint32_t d_main = tmem_base + (uint32_t)(acc * 2 * ACC_BN);
       const uint32_t d_small = d_main + (uint32_t)cross_off;
       for (int64_t kb = kb0; kb < kb1; ++kb) {
+        if (g.trace != nullptr && elect_one()) trace_ev(g.trace, 1, tcount, 15, (unsigned)kb);
         mbar_wait_uniform(&conv_bar[stage], phase);
+        if (g.trace != nullptr && elect_one()) trace_ev(g.trace, 1, tcount, 16, (unsigned)kb);
         tc_fence_after();
         if (elect_one()) {
           trace_ev(g.trace, 1, tcount, 4, (unsigned)kb);
@@ -551,7 +562,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int ct = threadIdx.x - 128;       // 0..255
     int stage = 0;
     uint32_t phase = 0;
-    const int nvec = raw_bytes / 16;
+    const int nvec = (g.b_lo_tma ? A_BYTES : raw_bytes) / 16;
     if constexpr (VER == 2) {
       // Two groups of 4 warps take alternate k-blocks.  Thread = one tile row (its warp's TMEM lane quadrant):
       // 16 raw fp32 of the row -> hi (masked bits) and lo = tf32_rn(x - hi) -> two tcgen05.st.x16 into the TMEM
@@ -560,7 +571,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int q = warp & 3;
       const int row = q * 32 + lane;
       const int gt = ct - grp * 128;          // 0..127 inside the group
-      const int nvb = b_bytes / 16;
+      const int nvb = g.b_lo_tma ? 0 : b_bytes / 16;
       constexpr int MAXVB = ACC_BN * BK * 4 / 16 / 128;   // 3
       int astage = 0;
       uint32_t aphase = 0;
@@ -810,6 +821,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
 }
 
+// lo plane of a whole matrix: dst = tf32_rn(x - trunc_tf32(x)), bit-identical to the in-kernel converters
+__global__ void __launch_bounds__(256) split_lo_kernel(const float4* __restrict__ src, float4* __restrict__ dst, int64_t nvec) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 x = src[i];
+    float4 l;
+    l.x = tf32_rna_f(x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u));
+    l.y = tf32_rna_f(x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u));
+    l.z = tf32_rna_f(x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u));
+    l.w = tf32_rna_f(x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u));
+    dst[i] = l;
+  }
+}
+// caller-owned scratch for the precomputed B_lo plane (krs_gemm_set_workspace); calls that use it must be issued
+// on one stream at a time
+struct Workspace { void* ptr; size_t bytes; int device; };
+std::mutex g_ws_mu;
+Workspace g_ws_val{nullptr, 0, -1};
+Workspace get_ws() { std::lock_guard<std::mutex> l(g_ws_mu); return g_ws_val; }
+
 // ---------------------------------------------------------------- host side
 PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -851,7 +881,7 @@ bool make_map_3d(CUtensorMap* map, const float* base, int64_t rows, int64_t cols
   return r == CUDA_SUCCESS;
 }
 
-using TcKernel = void (*)(const CUtensorMap, const CUtensorMap, const TcArgs);
+using TcKernel = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcArgs);
 template <int VER>
 TcKernel kernel_table_v(int kind, int act) {
   switch (kind) {
@@ -931,13 +961,34 @@ int gemm_tc(const float* A, int64_t lda, bool transA, const float* B, int64_t ld
   if (const char* e = getenv("KRS_TC_MN_LBO")) g.mn_lbo = atoi(e);       // debug overrides
   if (const char* e = getenv("KRS_TC_MN_SBO")) g.mn_sbo = atoi(e);
   if (const char* e = getenv("KRS_TC_MN_KSTEP")) g.mn_kstep = atoi(e);
-  g.fuse_n = 0;
+  g.fuse_n = 1;
   if (const char* e = getenv("KRS_TC_FUSE_N")) g.fuse_n = atoi(e);
   if (2 * g.bn > 256) g.fuse_n = 0;
+  // B_lo plane precomputed once per call into the caller-registered workspace when B is small and re-read by many
+  // m-tiles (weights): the converters then touch only the A tile (28 -> 16 elements and 10 -> 4 shared-memory
+  // instructions per thread and k-block in VER 2)
+  g.b_lo_tma = 0;
+  const float* B_lo = nullptr;
+  {
+    const int64_t b_rows = transB ? N : K;
+    const size_t b_plane = (size_t)b_rows * (size_t)ldb * sizeof(float);
+    Workspace w = get_ws();
+    int cur_dev = -1;
+    bool want = w.ptr != nullptr && b_plane <= w.bytes && M >= 4 * N && cudaGetDevice(&cur_dev) == cudaSuccess &&
+                cur_dev == w.device;
+    if (const char* e = getenv("KRS_TC_B_LO_TMA")) want = want && atoi(e) != 0;
+    if (want) {
+      split_lo_kernel<<<(unsigned)imin<int64_t>(2 * sm_count(), ceil_div<int64_t>((int64_t)(b_plane / 16), 256)), 256, 0, stream>>>(
+          reinterpret_cast<const float4*>(B), reinterpret_cast<float4*>(w.ptr), (int64_t)(b_plane / 16));
+      KRS_LAUNCH_CHECK();
+      B_lo = reinterpret_cast<const float*>(w.ptr);
+      g.b_lo_tma = 1;
+    }
+  }
   // VER 2: the MN-major A tile is only read by converter threads (consecutive lanes = consecutive words): no swizzle
   const int a_mn_swz = ver == 2 ? (int)CU_TENSOR_MAP_SWIZZLE_NONE : mn_swz;
 
-  CUtensorMap ma, mb;
+  CUtensorMap ma, mb, mblo;
   bool ok;
   g.a_3d = g.b_3d = 0;
   const bool allow3d = getenv("KRS_TC_NO_3D") == nullptr;
@@ -955,6 +1006,14 @@ int gemm_tc(const float* A, int64_t lda, bool transA, const float* B, int64_t ld
     else ok = make_map(&mb, B, K, N, ldb, 32, BK, (CUtensorMapSwizzle)mn_swz);                   // [K][N]
   }
   if (!ok) return KRS_EUNSUPPORTED;
+  if (g.b_lo_tma) {
+    if (!g.b_mn_major) ok = make_map(&mblo, B_lo, N, K, ldb, BK, g.bn, CU_TENSOR_MAP_SWIZZLE_64B);
+    else if (g.b_3d) ok = make_map_3d(&mblo, B_lo, K, N, ldb, g.bn / 32, (CUtensorMapSwizzle)mn_swz);
+    else ok = make_map(&mblo, B_lo, K, N, ldb, 32, BK, (CUtensorMapSwizzle)mn_swz);
+    if (!ok) return KRS_EUNSUPPORTED;
+  } else {
+    mblo = mb;
+  }
 
   if (g.atomic_out && !accumulate)
     KRS_CUDA(cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, stream));
@@ -987,7 +1046,7 @@ int gemm_tc(const float* A, int64_t lda, bool transA, const float* B, int64_t ld
   const int actc = !has_act ? TA_LINEAR : (epi.act == KRS_ACT_LINEAR ? TA_LINEAR : (epi.act == KRS_ACT_RELU ? TA_RELU : TA_GENERIC));
   TcKernel kfn = kernel_table(ver == 2 ? 2 : 1, kind, actc);
   KRS_REQUIRE(kfn != nullptr, "gemm_tc: no kernel for kind %d act %d", kind, actc);
-  kfn<<<grid, NUM_THREADS, smem, stream>>>(ma, mb, g);
+  kfn<<<grid, NUM_THREADS, smem, stream>>>(ma, mb, mblo, g);
   KRS_LAUNCH_CHECK();
   g_tc_launches.fetch_add(1);
   return KRS_OK;
@@ -996,6 +1055,24 @@ int gemm_tc(const float* A, int64_t lda, bool transA, const float* B, int64_t ld
 void gemm_tc_set_trace(unsigned long long* p) { g_trace.store(p); }
 }  // namespace krs
 
+extern "C" int krs_gemm_set_workspace(void* dev_buf, size_t bytes) {
+  if (dev_buf != nullptr && !krs::aligned16(dev_buf)) {
+    krs::set_error("krs_gemm_set_workspace: buffer must be 16-byte aligned");
+    return KRS_EINVAL;
+  }
+  int dev = -1;
+  if (dev_buf != nullptr) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, dev_buf) != cudaSuccess || at.type != cudaMemoryTypeDevice) {
+      (void)cudaGetLastError();
+      krs::set_error("krs_gemm_set_workspace: not a device pointer");
+      return KRS_EINVAL;
+    }
+    dev = at.device;
+  }
+  { std::lock_guard<std::mutex> l(krs::g_ws_mu); krs::g_ws_val = krs::Workspace{dev_buf, dev_buf ? bytes : 0, dev}; }
+  return KRS_OK;
+}
 extern "C" long long krs_gemm_tc_launch_count(void) { return krs::gemm_tc_launches(); }
 extern "C" int krs_gemm_tc_set_trace(void* dev_buf) {
   krs::gemm_tc_set_trace(reinterpret_cast<unsigned long long*>(dev_buf));

@@ -18,9 +18,26 @@ def _c(t: torch.Tensor) -> torch.Tensor:
     return t if t.is_contiguous() else t.contiguous()
 
 
+_GEMM_WS: dict[int, torch.Tensor] = {}    # device index -> scratch registered with krs_gemm_set_workspace
+
+
+def ensure_gemm_workspace(nbytes: int = 32 << 20) -> None:
+    """Registers a caller-owned scratch buffer for the tcgen05 engines (precomputed low-order TF32 plane of small B
+    operands, include/krs_b200.h krs_gemm_set_workspace).  One buffer per process/device, allocated once."""
+    if not torch.cuda.is_available():
+        return
+    dev = torch.cuda.current_device()
+    if dev not in _GEMM_WS:
+        _GEMM_WS[dev] = torch.empty(nbytes, dtype=torch.uint8, device=f"cuda:{dev}")
+    check(lib.krs_gemm_set_workspace(_GEMM_WS[dev].data_ptr(), _GEMM_WS[dev].numel()))
+
+
 def set_gemm_engine(name: str) -> None:
-    """'ffma' (exact fp32 FMA products) or 'tcgen05' (tensor pipe, 3xTF32 split)."""
+    """'ffma' (exact fp32 FMA products), 'tcgen05' (tensor pipe, 3xTF32 split, operands from shared memory) or
+    'tcgen05_ts' (same, A operand kept in tensor memory)."""
     check(lib.krs_set_gemm_engine({"ffma": 0, "tcgen05": 1, "tcgen05_ts": 2}[name]))
+    if name != "ffma":
+        ensure_gemm_workspace()
 
 
 def get_gemm_engine() -> str:

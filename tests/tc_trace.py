@@ -41,7 +41,7 @@ for role in range(4):
         if c: ev.append((a >> 32, a & 0xffffffff, c))
 ev.sort(key=lambda e: e[2]); t0 = ev[0][2]
 names = {1: "TMA issued", 2: "conv saw full", 9: "conv fence done / (ts) A stage free", 8: "conv stores issued", 3: "conv done",
-         4: "mma saw conv", 5: "mma committed", 6: "epi start", 7: "epi done"}
+         4: "mma saw conv", 5: "mma committed", 6: "epi start", 7: "epi done", 15: "mma loop top", 16: "mma wait done"}
 print("entries", len(ev))
 by = {k: [(i, c - t0) for tag, i, c in ev if tag == k] for k in names}
 for k in (6, 7):
@@ -60,13 +60,16 @@ def med(a, b2, keys=None):
     d = [b2[k] - a[k] for k in keys if k in a and k in b2]
     return float(np.median(d)) if d else float("nan")
 for tile in (0, 1, 2):
-    T = {k: per_tile(k, tile) for k in (1, 2, 9, 8, 3, 4, 5)}
+    T = {k: per_tile(k, tile) for k in (1, 2, 9, 8, 3, 4, 5, 15, 16)}
     if len(T[5]) < KB: break
     c5 = [T[5][k] for k in sorted(T[5])]
     print(f"tile {tile}: mainloop {c5[-1] - T[4][0]} clks; k-block period (mma committed) median {np.median(np.diff(c5)):.0f}; "
           f"TMA issue->conv saw full {med(T[1], T[2]):.0f}; conv: full->(9) {med(T[2], T[9]):.0f}, (9)->stores issued {med(T[9], T[8]):.0f}, "
           f"full->stores issued {med(T[2], T[8]):.0f}, stores->done {med(T[8], T[3]):.0f}, full->done {med(T[2], T[3]):.0f}; "
           f"conv done->mma saw {med(T[3], T[4]):.0f}; mma saw->committed {med(T[4], T[5]):.0f}")
+    nxt = {k: T[15].get(k + 1) for k in T[5]}
+    print(f"   mma warp: loop top->wait done {med(T[15], T[16]):.0f}; wait done->(fence, elect) tag 4 {med(T[16], T[4]):.0f}; issue (4->5) {med(T[4], T[5]):.0f}; "
+          f"5->next loop top {np.median([nxt[k] - T[5][k] for k in T[5] if nxt.get(k)]):.0f}")
     ks = sorted(T[2])[:8]
     print("   traced conv k-blocks", ks, " TMA", [T[1].get(k) for k in ks], " full", [T[2].get(k) for k in ks], " convdone", [T[3].get(k) for k in ks],
           " mma saw", [T[4].get(k) for k in ks], " commit", [T[5].get(k) for k in ks])

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 
 
 # engines under test: "tcgen05" (SS operands) and "tcgen05_ts" (A operand in tensor memory)
-ENGINES = [e for e in os.environ.get("KRS_TEST_TC_ENGINES", "tcgen05").split(",") if e]
+ENGINES = [e for e in os.environ.get("KRS_TEST_TC_ENGINES", "tcgen05,tcgen05_ts").split(",") if e]
 
 
 @pytest.fixture(params=ENGINES)
