@@ -177,6 +177,11 @@ int krs_dot_bwd(const float* const* feats, const int64_t* strides, const float* 
  * Q (nq,d), C (nc,d), cand_ids nullable int32 (nc).  top_scores (nq,k) fp32, top_ids (nq,k) int32.
  * workspace: krs_topk_workspace_bytes(). */
 size_t krs_topk_workspace_bytes(int64_t nq, int64_t nc, int d, int k);
+/* Score engine of krs_topk: 0 = auto (tensor pipe when the problem fills the machine and the shape is eligible:
+ * d % 4 == 0, d <= 64, k <= 128, nc >= 96), 1 = exact-fp32 FMA score tiles only, 2 = tcgen05 (3xTF32, fp32-level
+ * accuracy) whenever eligible.  krs_topk_tc_launch_count() lets tests prove which kernel produced a result. */
+int krs_set_topk_engine(int engine);
+long long krs_topk_tc_launch_count(void);
 int krs_topk(const float* Q, const float* C, const int32_t* cand_ids, float* top_scores,
              int32_t* top_ids, int64_t nq, int64_t nc, int d, int k, void* workspace,
              size_t workspace_bytes, void* stream);

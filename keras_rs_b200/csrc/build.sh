@@ -9,7 +9,7 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompil
 SRCS=(api gemm_ffma gemm_tc cross_dense gather optim dot topk shard)
 pids=()
 for s in "${SRCS[@]}"; do
-  if [ ! -f "$HERE/obj/$s.o" ] || [ "$HERE/$s.cu" -nt "$HERE/obj/$s.o" ] || [ "$HERE/common.cuh" -nt "$HERE/obj/$s.o" ] || [ "$HERE/../../include/krs_b200.h" -nt "$HERE/obj/$s.o" ]; then
+  if [ ! -f "$HERE/obj/$s.o" ] || [ "$HERE/$s.cu" -nt "$HERE/obj/$s.o" ] || [ "$HERE/common.cuh" -nt "$HERE/obj/$s.o" ] || [ "$HERE/tc_common.cuh" -nt "$HERE/obj/$s.o" ] || [ "$HERE/../../include/krs_b200.h" -nt "$HERE/obj/$s.o" ]; then
     ( "$NVCC" "${FLAGS[@]}" -c "$HERE/$s.cu" -o "$HERE/obj/$s.o" > "$HERE/obj/$s.log" 2>&1 || { cat "$HERE/obj/$s.log"; exit 1; } ) &
     pids+=($!)
   fi

@@ -40,9 +40,11 @@
 #include <mutex>
 
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace krs {
 namespace {
+using namespace tcx;
 
 constexpr int BM = 128;          // rows per tile == TMEM lanes
 constexpr int BK = 16;           // fp32 elements per k-block (64 B)
@@ -55,7 +57,6 @@ constexpr int EPI_LD = 36;                // staging row pitch in floats (32 + 4
 constexpr int EPI_SMEM_BYTES = 4 * 32 * EPI_LD * 4;   // one 32x32 staging tile per epilogue warp
 constexpr int A_BYTES = BM * BK * 4;             // 8192
 constexpr int KC_MAX = 1024;                     // max K elements accumulated inside one TMEM tile
-constexpr int SPIN_LIMIT = 1 << 26;              // turns a protocol bug into a trap instead of a hang
 // Kernel versions.  VER 1: both operands read by the tensor core from shared memory (SS), converters write
 // A_lo / B_lo tiles to shared memory.  VER 2: the A operand (hi and lo) lives in TENSOR MEMORY (TS): converter
 // threads own one tile row each, read it from the TMA-landed raw tile, split it in registers and tcgen05.st the
@@ -88,6 +89,7 @@ struct TcArgs {
   int no_mask;            // 1: leave hi = raw fp32 bits (hardware ignores the low 13 mantissa bits)
   int mn_lbo, mn_sbo, mn_kstep, mn_layout;   // MN-major descriptor strides (bytes) and UMMA layout type
   int fuse_n;             // one N = 2*bn MMA computes A_hi x [B_hi | B_lo] (main and hi*lo terms together)
+  uint32_t wait_ns;       // suspend-time hint of the critical-path mbarrier waits
   int b_lo_tma;           // B_lo comes precomputed from global memory by TMA (tmap_blo); converters skip the B tile
   Epilogue epi;
 };
@@ -102,156 +104,6 @@ __device__ __forceinline__ void trace_ev(const unsigned long long* tr_c, int rol
   ++count;
 }
 
-// ---------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// Critical-path wait: try_wait with a suspend-time hint compiles to TRYWAIT + NANOSLEEP.SYNCS — the warp is
-// parked by the hardware and woken by the barrier's phase change, so a waiting role does not burn issue slots
-// that lower-priority warps (the epilogue) need.  A tight try_wait spin starved them (tests/tc_trace.py).
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t ok = 0;
-  int spins = 0;
-  while (true) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x400;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (ok) break;
-    if (++spins > SPIN_LIMIT) __trap();
-  }
-}
-// Long waits (producer on a free stage, epilogue on the accumulator) back off with nanosleep: a spinning
-// warp steals issue slots from the converter warps that share its scheduler (ncu, profiles/r1_gemm_tc.md).
-__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t ok = 0;
-  int spins = 0;
-  while (true) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x2000;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (ok) break;
-    __nanosleep(128);
-    if (++spins > SPIN_LIMIT) __trap();
-  }
-}
-// one lane of a converged warp (elect.sync); the elected branch keeps warp-uniform operands in uniform registers
-__device__ __forceinline__ uint32_t elect_one() {
-  uint32_t pred = 0;
-  asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred));
-  return pred;
-}
-// mbar_wait for a fully converged warp whose later code must stay provably uniform: the loop exit is a warp vote
-__device__ __forceinline__ void mbar_wait_uniform(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  int spins = 0;
-  while (true) {
-    uint32_t ok = 0;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x400;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (__all_sync(0xffffffffu, ok != 0)) break;
-    if (++spins > SPIN_LIMIT) __trap();
-  }
-}
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-          smem_u32(smem_dst)),
-      "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
-          smem_u32(smem_dst)),
-      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
-      : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// A operand from tensor memory (lane = tile row, one 32-bit column per k element), B by shared-memory descriptor
-__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem),
-      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
-      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
-      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
-}
-__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// UMMA shared-memory descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor; version = 1 on sm_100).
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;                    // version
-  d |= (uint64_t)(layout_type & 7) << 61;    // 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
-  return d;
-}
-// K-major tile: rows of 64 B (BK floats), SWIZZLE_64B, 8-row groups 512 B apart; k-step = +32 B.
-__device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile_addr, int kstep) {
-  return make_desc(tile_addr + kstep * 32, 16, 512, 4);
-}
 // MN-major tile (32-bit elements): blocks of 32 mn x 16 k (2048 B).  For tf32 the ONLY MN-major layout
 // the tensor core accepts is SWIZZLE_128B_BASE32B (layout type 1; cutlass sm100_common.inl:92): 32-byte
 // chunks swizzled within a 128-byte row over groups of 4 k-rows — TMA mode SWIZZLE_128B_ATOM_32B.
@@ -260,11 +112,6 @@ __device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile_addr, int kstep, 
   return make_desc(tile_addr + kstep * g.mn_kstep, g.mn_lbo, g.mn_sbo, (uint32_t)g.mn_layout);
 }
 
-__device__ __forceinline__ float tf32_rna_f(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
 
 // ---------------------------------------------------------------- fused epilogue on one float4 (4 columns of one row)
 // Called AFTER the accumulator chunk has been transposed through shared memory, so that a warp instruction
@@ -444,7 +291,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         // the whole (converged) warp polls, ONE elected lane arms the transaction count and issues every box of
         // the stage with warp-uniform coordinates (UTMALDG takes uniform registers: per-lane boxes were compiled
         // into R2UR + ELECT / BRA.U.ANY waterfall loops)
-        mbar_wait_uniform(&empty_bar[stage], phase ^ 1);
+        mbar_wait_uniform(&empty_bar[stage], phase ^ 1, g.wait_ns);
         unsigned char* st = smem + (size_t)stage * stage_bytes;
         const int k0 = (int)(kb * BK);
         if (elect_one()) {
@@ -500,7 +347,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const uint32_t d_small = d_main + (uint32_t)cross_off;
       for (int64_t kb = kb0; kb < kb1; ++kb) {
         if (g.trace != nullptr && elect_one()) trace_ev(g.trace, 1, tcount, 15, (unsigned)kb);
-        mbar_wait_uniform(&conv_bar[stage], phase);
+        mbar_wait_uniform(&conv_bar[stage], phase, g.wait_ns);
         if (g.trace != nullptr && elect_one()) trace_ev(g.trace, 1, tcount, 16, (unsigned)kb);
         tc_fence_after();
         if (elect_one()) {
@@ -584,7 +431,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int64_t kb1 = imin<int64_t>(g.kblocks_total, kb0 + g.kblocks_per_split);
         for (int64_t kb = kb0; kb < kb1; ++kb) {
           if ((int)(cnt & 1u) == grp) {
-            mbar_wait(&full_bar[stage], phase);
+            mbar_wait(&full_bar[stage], phase, g.wait_ns);
             if (ct == 0) trace_ev(g.trace, 2, tcount, 2, (unsigned)kb);
             const unsigned char* st = smem + (size_t)stage * stage_bytes;
             uint32_t a[16];
@@ -614,7 +461,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               hi[k] = a[k] & 0xFFFFE000u;
               lo[k] = __float_as_uint(tf32_rna_f(__uint_as_float(a[k]) - __uint_as_float(hi[k])));
             }
-            mbar_wait(&afree_bar[astage], aphase ^ 1);     // MMAs of the k-block that used this A stage are done
+            mbar_wait(&afree_bar[astage], aphase ^ 1, g.wait_ns);     // MMAs of the k-block that used this A stage are done
             tc_fence_after();
             if (ct == 0) trace_ev(g.trace, 2, tcount, 9, (unsigned)kb);
             const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(Cfg<VER>::A_COL0 + astage * 32);
@@ -652,7 +499,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int64_t kb0 = (int64_t)split * g.kblocks_per_split;
       const int64_t kb1 = imin<int64_t>(g.kblocks_total, kb0 + g.kblocks_per_split);
       for (int64_t kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+        mbar_wait(&full_bar[stage], phase, g.wait_ns);
         if (ct == 0) trace_ev(g.trace, 2, tcount, 2, (unsigned)kb);
         float4* raw = reinterpret_cast<float4*>(smem + (size_t)stage * stage_bytes);
         float4* lo = reinterpret_cast<float4*>(smem + (size_t)stage * stage_bytes + raw_bytes);
@@ -841,32 +688,6 @@ Workspace g_ws_val{nullptr, 0, -1};
 Workspace get_ws() { std::lock_guard<std::mutex> l(g_ws_mu); return g_ws_val; }
 
 // ---------------------------------------------------------------- host side
-PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
-  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
-  if (fn == nullptr) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
-  }
-  return fn;
-}
-
-// Row-major matrix [rows][cols] (cols contiguous, leading dimension ld).  box = {box_cols, box_rows}.
-bool make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows,
-              CUtensorMapSwizzle swz) {
-  auto fn = encode_fn();
-  if (!fn) return false;
-  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
-  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS;
-}
-
 // MN-contiguous matrix [rows = K][cols = MN] viewed as 3-D {32, K, MN/32}: one box {32, BK, blocks} lands in
 // shared memory as `blocks` consecutive [BK rows x 128 B] sub-tiles — exactly the MN-major UMMA layout.
 bool make_map_3d(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int blocks, CUtensorMapSwizzle swz) {
@@ -967,6 +788,8 @@ int gemm_tc(const float* A, int64_t lda, bool transA, const float* B, int64_t ld
   // B_lo plane precomputed once per call into the caller-registered workspace when B is small and re-read by many
   // m-tiles (weights): the converters then touch only the A tile (28 -> 16 elements and 10 -> 4 shared-memory
   // instructions per thread and k-block in VER 2)
+  g.wait_ns = 0x400;
+  if (const char* e = getenv("KRS_TC_WAIT_NS")) g.wait_ns = (uint32_t)atoi(e);
   g.b_lo_tma = 0;
   const float* B_lo = nullptr;
   {

@@ -349,6 +349,11 @@ def dot_interaction(inputs, self_interaction: bool, skip_gather: bool):
 
 
 # ----------------------------------------------------------------------------- retrieval
+def set_topk_engine(name: str) -> None:
+    """'auto' (tensor pipe for large problems), 'ffma' (exact-fp32 FMA score tiles) or 'tcgen05' (whenever eligible)."""
+    check(lib.krs_set_topk_engine({"auto": 0, "ffma": 1, "tcgen05": 2}[name]))
+
+
 def top_k_scores(q: torch.Tensor, cand: torch.Tensor, cand_ids: torch.Tensor | None, k: int):
     """Streaming Q @ C^T + exact top-k (never materialises the score matrix)."""
     q = _c(q)

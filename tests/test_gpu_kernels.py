@@ -408,24 +408,53 @@ def _check_topk(scores_ref, got_s, got_i, k, tol=2e-5):
         assert len(set(got_i[r].tolist())) == k
 
 
-@pytest.mark.parametrize("nq,nc,d,k", [(33, 5000, 64, 100), (200, 20000, 32, 10), (7, 300, 20, 128), (64, 129, 128, 5)])
-def test_topk_vs_oracle(K, nq, nc, d, k):
+@pytest.fixture(params=["ffma", "tcgen05"])
+def topk_engine(request, K):
+    K.ops.set_topk_engine(request.param)
+    yield request.param
+    K.ops.set_topk_engine("auto")
+
+
+@pytest.mark.parametrize("nq,nc,d,k", [(33, 5000, 64, 100), (200, 20000, 32, 10), (7, 300, 20, 128), (64, 129, 128, 5),
+                                       (300, 40000, 64, 100), (129, 3000, 48, 1), (5, 97, 8, 96)])
+def test_topk_vs_oracle(K, topk_engine, nq, nc, d, k):
     rng = np.random.default_rng(nq + nc)
     q = rng.normal(size=(nq, d)).astype(np.float32)
     c = rng.normal(size=(nc, d)).astype(np.float32)
+    before = K._lib.lib.krs_topk_tc_launch_count()
     s, i = K.ops.top_k_scores(dev(q), dev(c), None, k)
+    ran_tc = K._lib.lib.krs_topk_tc_launch_count() - before
+    eligible = d % 4 == 0 and d <= 64 and nc >= 96
+    assert ran_tc == (1 if (topk_engine == "tcgen05" and eligible) else 0)
     ref = (q.astype(np.float64) @ c.astype(np.float64).T)
     _check_topk(ref, npy(s), npy(i), k)
     assert (np.diff(npy(s), axis=1) <= 0).all()                     # sorted descending
 
 
-def test_topk_ties_lowest_index_first(K):
+def test_topk_ties_lowest_index_first(K, topk_engine):
     c = np.zeros((300, 8), np.float32)
     c[:, 0] = 1.0
     c[10, 0] = 2.0
     q = np.ones((3, 8), np.float32)
     s, i = K.ops.top_k_scores(dev(q), dev(c), None, 6)
     assert npy(i).tolist() == [[10, 0, 1, 2, 3, 4]] * 3           # jax.lax.top_k tie rule
+
+
+def test_topk_tc_candidate_ids_and_large_slice(K):
+    """tensor-pipe path with candidate ids, several slices per query tile and a ragged last tile."""
+    K.ops.set_topk_engine("tcgen05")
+    try:
+        rng = np.random.default_rng(9)
+        nq, nc, d, k = 260, 100_003, 64, 50
+        q = rng.normal(size=(nq, d)).astype(np.float32)
+        c = rng.normal(size=(nc, d)).astype(np.float32)
+        ids = (np.arange(nc, dtype=np.int64) * 7 + 11).astype(np.int32)
+        s, i = K.ops.top_k_scores(dev(q), dev(c), dev(ids), k)
+        ref = q.astype(np.float64) @ c.astype(np.float64).T
+        raw = (npy(i).astype(np.int64) - 11) // 7
+        _check_topk(ref, npy(s), raw, k)
+    finally:
+        K.ops.set_topk_engine("auto")
 
 
 def test_retrieval_shared_variable_pattern(K):
