@@ -251,9 +251,17 @@ constexpr int T_QCOL0 = 4 * TNC;        // TMEM columns of the parked query tile
 constexpr int T_THREADS = 512;
 constexpr int T_MAX_STAGES = 16;
 
+// order-preserving float <-> int key (involution), so that atomicMax on ints orders scores
+__device__ __forceinline__ int score_key(float x) {
+  const int b = __float_as_int(x);
+  return b >= 0 ? b : (b ^ 0x7fffffff);
+}
+__device__ __forceinline__ float key_score(int key) { return __int_as_float(key >= 0 ? key : (key ^ 0x7fffffff)); }
+
 struct TopkTcArgs {
   float* part_s;
   int32_t* part_i;
+  int* g_bound;          // [nq] best k-th score any slice has reached so far (score_key), a lower bound of the final k-th
   int64_t nq, nc;
   int d, k, S, KB, stages;
   int q_tiles;
@@ -266,10 +274,8 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int STAGES = a.stages;
   const int k = a.k;
-  float* list_s = reinterpret_cast<float*>(smem + (size_t)STAGES * T_STAGE);       // [TQ][k]
-  int* list_i = reinterpret_cast<int*>(list_s + (size_t)TQ * k);                   // [TQ][k]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(list_i + (size_t)TQ * k);
-  // (TQ * k * 8 is a multiple of 8, so the barriers stay 8-byte aligned)
+  long long* list_k = reinterpret_cast<long long*>(smem + (size_t)STAGES * T_STAGE);   // [TQ][k] packed (score, index) keys
+  uint64_t* bars = reinterpret_cast<uint64_t*>(list_k + (size_t)TQ * k);
   uint64_t* full_bar = bars;                       // [STAGES] TMA landed
   uint64_t* conv_bar = bars + T_MAX_STAGES;        // [STAGES] converter group done
   uint64_t* empty_bar = bars + 2 * T_MAX_STAGES;   // [STAGES] MMAs that read the entry have completed
@@ -453,8 +459,11 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     }
   } else if (warp < 4) {
     // ======================= selection (warps 0..3; lane = query row = TMEM lane) =======================
-    float* ls_w = list_s + (size_t)(warp * 32) * k;
-    int* li_w = list_i + (size_t)(warp * 32) * k;
+    // A list entry is ONE 64-bit key: (score_key << 32) | (0xFFFFFFFF - candidate index); a larger key is a better
+    // entry (higher score, ties -> lower index), so the total order is a single integer comparison and an insert
+    // moves half as many shared-memory words as separate score / index arrays.
+    long long* lk_w = list_k + (size_t)(warp * 32) * k;
+    constexpr long long EMPTY = LLONG_MIN;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int64_t item = blockIdx.x; item < a.n_items; item += gridDim.x) {
@@ -462,64 +471,82 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       const int qt = (int)(item - sl * a.q_tiles);
       const int64_t t0 = sl * a.tiles_per_slice;
       const int64_t t1 = imin<int64_t>(a.ntiles, t0 + a.tiles_per_slice);
-      for (int idx = lane; idx < 32 * k; idx += 32) {
-        ls_w[idx] = -INFINITY;
-        li_w[idx] = INT_MAX;
-      }
+      for (int idx = lane; idx < 32 * k; idx += 32) lk_w[idx] = EMPTY;
       __syncwarp();
-      float th = -INFINITY;          // running k-th best of THIS lane's query
+      // th = max(k-th best of this slice's list, best k-th ANY slice of this query has published): a candidate below
+      // either bound cannot be in the final top-k, so the slices prune each other (without this every slice warms
+      // up from -inf and the list inserts, each several dependent shared-memory round trips, dominate)
+      float th = -INFINITY;
+      const int64_t q_me = (int64_t)qt * TQ + warp * 32 + lane;
+      int published = INT_MIN;
       for (int64_t tile = t0; tile < t1; ++tile) {
+        if (q_me < a.nq) th = fmaxf(th, key_score(*reinterpret_cast<volatile int*>(a.g_bound + q_me)));
         mbar_wait_relaxed(&tmem_full[acc], acc_phase);
         tc_fence_after();
         const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * 2 * TNC);
         const int64_t c0 = tile * TNC;
+        const int nvalid = (int)imin<int64_t>(TNC, a.nc - c0);       // candidates of this tile that exist
         for (int ch = 0; ch < TNC / 16; ++ch) {
           uint32_t r[16], r2[16];
           tc_ld16(t_row + (uint32_t)(ch * 16), r);
           tc_ld16(t_row + (uint32_t)(TNC + ch * 16), r2);
           tc_wait_ld();
+          float v[16];
+          uint32_t mk = 0;                                 // bit j: score j of this lane's query passes the threshold
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float v = __fadd_rn(__uint_as_float(r[j]), __uint_as_float(r2[j]));
-            const int64_t cand = c0 + ch * 16 + j;
-            unsigned m = __ballot_sync(0xffffffffu, cand < a.nc && v >= th);
-            while (m) {
-              const int src = __ffs(m) - 1;
-              m &= m - 1;
-              const float sc = __shfl_sync(0xffffffffu, v, src);
-              const int ci = (int)cand;
-              float* ls = ls_w + (size_t)src * k;
-              int* li = li_w + (size_t)src * k;
-              float cs[4];
-              int cix[4];
-              int pos = 0;
+            v[j] = __fadd_rn(__uint_as_float(r[j]), __uint_as_float(r2[j]));
+            mk |= (v[j] >= th) ? (1u << j) : 0u;
+          }
+          const int nv = nvalid - ch * 16;
+          if (nv < 16) mk &= nv <= 0 ? 0u : ((1u << nv) - 1u);
+          unsigned any = __ballot_sync(0xffffffffu, mk != 0u);
+          while (any) {                                    // survivors are rare: one warp-cooperative insert each
+            const int src = __ffs(any) - 1;
+            const int jj = __ffs(mk) - 1;                  // meaningful on lane src
+            float sc_l = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) sc_l = (j == jj) ? v[j] : sc_l;
+            const float sc = __shfl_sync(0xffffffffu, sc_l, src);
+            const int jb = __shfl_sync(0xffffffffu, jj, src);
+            const int ci = (int)(c0 + ch * 16 + jb);
+            const long long key = ((long long)score_key(sc) << 32) | (long long)(0xFFFFFFFFu - (uint32_t)ci);
+            long long* lk = lk_w + (size_t)src * k;
+            long long cur[4];
+            int pos = 0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const int x = lane + 32 * c;
+              cur[c] = x < k ? lk[x] : EMPTY;
+              pos += __popc(__ballot_sync(0xffffffffu, x < k && cur[c] > key));
+            }
+            float kth = -INFINITY;
+            if (pos < k) {                                 // warp-uniform
+              __syncwarp();
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
                 const int x = lane + 32 * c;
-                const bool in = x < k;
-                cs[c] = in ? ls[x] : -INFINITY;
-                cix[c] = in ? li[x] : INT_MAX;
-                pos += __popc(__ballot_sync(0xffffffffu, in && beats(cs[c], cix[c], sc, ci)));
+                if (x >= pos && x + 1 < k) lk[x + 1] = cur[c];
               }
-              if (pos < k) {               // warp-uniform
-                __syncwarp();
+              if (lane == 0) lk[pos] = key;
+              __syncwarp();
+              const long long kk = lk[k - 1];
+              if (kk != EMPTY) kth = key_score((int)(kk >> 32));
+            }
+            if (lane == src) {
+              mk &= mk - 1;                                // this candidate is done
+              if (kth > th) {
+                th = kth;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                  const int x = lane + 32 * c;
-                  if (x >= pos && x + 1 < k) {
-                    ls[x + 1] = cs[c];
-                    li[x + 1] = cix[c];
-                  }
+                for (int j = 0; j < 16; ++j) mk &= (v[j] >= th) ? 0xFFFFFFFFu : ~(1u << j);   // re-filter what is left
+                const int pkey = score_key(kth);
+                if (pkey > published && q_me < a.nq) {
+                  atomicMax(a.g_bound + q_me, pkey);
+                  published = pkey;
                 }
-                if (lane == 0) {
-                  ls[pos] = sc;
-                  li[pos] = ci;
-                }
-                __syncwarp();
-                const float kth = ls[k - 1];
-                if (lane == src) th = kth;
               }
             }
+            any = __ballot_sync(0xffffffffu, mk != 0u);
           }
         }
         tc_fence_before();
@@ -534,8 +561,9 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         if (qg < a.nq) {
           const int64_t o = (qg * a.S + sl) * k;
           for (int r = lane; r < k; r += 32) {
-            a.part_s[o + r] = ls_w[(size_t)qq * k + r];
-            a.part_i[o + r] = li_w[(size_t)qq * k + r];
+            const long long kk = lk_w[(size_t)qq * k + r];
+            a.part_s[o + r] = kk == EMPTY ? -INFINITY : key_score((int)(kk >> 32));
+            a.part_i[o + r] = kk == EMPTY ? INT_MAX : (int)(0xFFFFFFFFu - (uint32_t)(kk & 0xFFFFFFFFll));
           }
         }
       }
@@ -629,7 +657,7 @@ extern "C" size_t krs_topk_workspace_bytes(int64_t nq, int64_t nc, int d, int k)
   int S = choose_splits(nq, nc, k);
   const TcPlan p = plan_tc(nq, nc, d, k);
   if (p.ok && p.S > S) S = p.S;       // large enough for either engine
-  return (size_t)nq * S * k * (sizeof(float) + sizeof(int32_t));
+  return (size_t)nq * S * k * (sizeof(float) + sizeof(int32_t)) + (p.ok ? (size_t)nq * sizeof(int) : 0);
 }
 
 extern "C" int krs_topk(const float* Q, const float* C, const int32_t* cand_ids, float* top_scores, int32_t* top_ids,
@@ -645,7 +673,7 @@ extern "C" int krs_topk(const float* Q, const float* C, const int32_t* cand_ids,
   cudaStream_t s = as_stream(stream);
   const TcPlan tp = plan_tc(nq, nc, d, k);
   if (use_tc(tp, nq, nc) && aligned16(Q) && aligned16(C)) {
-    const size_t need_tc = (size_t)nq * tp.S * k * (sizeof(float) + sizeof(int32_t));
+    const size_t need_tc = (size_t)nq * tp.S * k * (sizeof(float) + sizeof(int32_t)) + (size_t)nq * sizeof(int);
     KRS_REQUIRE(workspace && workspace_bytes >= need_tc, "krs_topk: workspace too small (%zu < %zu)", workspace_bytes, need_tc);
     CUtensorMap mq, mc;
     if (make_map(&mq, Q, nq, d, d, TKB, TQ, CU_TENSOR_MAP_SWIZZLE_64B) &&
@@ -653,6 +681,8 @@ extern "C" int krs_topk(const float* Q, const float* C, const int32_t* cand_ids,
       TopkTcArgs t;
       t.part_s = reinterpret_cast<float*>(workspace);
       t.part_i = reinterpret_cast<int32_t*>(t.part_s + (size_t)nq * tp.S * k);
+      t.g_bound = reinterpret_cast<int*>(t.part_i + (size_t)nq * tp.S * k);
+      KRS_CUDA(cudaMemsetAsync(t.g_bound, 0x80, (size_t)nq * sizeof(int), s));     // key 0x80808080 = below every score
       t.nq = nq; t.nc = nc; t.d = d; t.k = k; t.S = tp.S; t.KB = tp.KB; t.stages = tp.stages;
       t.q_tiles = tp.q_tiles; t.tiles_per_slice = tp.tiles_per_slice; t.ntiles = tp.ntiles; t.n_items = tp.n_items;
       KRS_CUDA(cudaFuncSetAttribute(topk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
