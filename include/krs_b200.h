@@ -53,6 +53,8 @@ int krs_gemm_tc_set_trace(void* dev_buf);
  * per call into this buffer and streamed by TMA instead of being re-derived per tile.  NULL / 0 unregisters.  The
  * buffer must outlive every GEMM call, and calls that use it must be issued on one stream at a time. */
 int krs_gemm_set_workspace(void* dev_buf, size_t bytes);
+/* Number of split_lo_kernel launches (the precomputed low-order plane above) so far in this process. */
+long long krs_gemm_split_launch_count(void);
 
 /* ------------------------------------------------------------------ activations
  * keras.activations used as FeatureCross.pre_activation / Dense.activation

@@ -57,6 +57,7 @@ _sig("krs_get_gemm_engine", C.c_int)
 _sig("krs_gemm_tc_launch_count", C.c_longlong)
 _sig("krs_gemm_tc_set_trace", C.c_int, C.c_void_p)
 _sig("krs_gemm_set_workspace", C.c_int, C.c_void_p, C.c_size_t)
+_sig("krs_gemm_split_launch_count", C.c_longlong)
 _sig("krs_gather_fwd", C.c_int, C.POINTER(KrsFeature), i32, i64, c_f32p, i64, i32, C.c_void_p)
 _sig("krs_gather_bwd", C.c_int, C.POINTER(KrsFeature), i32, i64, c_f32p, i64, C.c_void_p)
 _sig("krs_cross_fwd", C.c_int, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_float, i32, c_f32p, c_f32p,
@@ -95,7 +96,7 @@ _sig("krs_enable_peer_access", C.c_int, i32)
 
 EXPORTED = [
     "krs_version", "krs_last_error", "krs_device_sm_count", "krs_set_gemm_engine",
-    "krs_get_gemm_engine", "krs_gemm_tc_launch_count", "krs_gemm_tc_set_trace", "krs_gemm_set_workspace", "krs_gather_fwd", "krs_gather_bwd", "krs_cross_fwd", "krs_cross_bwd",
+    "krs_get_gemm_engine", "krs_gemm_tc_launch_count", "krs_gemm_tc_set_trace", "krs_gemm_set_workspace", "krs_gemm_split_launch_count", "krs_gather_fwd", "krs_gather_bwd", "krs_cross_fwd", "krs_cross_bwd",
     "krs_cross_combine_fwd", "krs_cross_combine_bwd", "krs_dense_fwd", "krs_dense_bwd", "krs_sgemm",
     "krs_dot_fwd", "krs_dot_bwd", "krs_topk_workspace_bytes", "krs_topk", "krs_set_topk_engine", "krs_topk_tc_launch_count", "krs_loss_fwd_bwd",
     "krs_adamw", "krs_adam_hyper_advance", "krs_sgd_adagrad", "krs_mod_route", "krs_ipc_alloc", "krs_ipc_open",

@@ -70,6 +70,7 @@ template <int VER> struct Cfg {
 };
 
 std::atomic<long long> g_tc_launches{0};
+std::atomic<long long> g_split_launches{0};
 std::atomic<unsigned long long*> g_trace{nullptr};
 
 struct TcArgs {
@@ -804,6 +805,7 @@ int gemm_tc(const float* A, int64_t lda, bool transA, const float* B, int64_t ld
       split_lo_kernel<<<(unsigned)imin<int64_t>(2 * sm_count(), ceil_div<int64_t>((int64_t)(b_plane / 16), 256)), 256, 0, stream>>>(
           reinterpret_cast<const float4*>(B), reinterpret_cast<float4*>(w.ptr), (int64_t)(b_plane / 16));
       KRS_LAUNCH_CHECK();
+      g_split_launches.fetch_add(1);
       B_lo = reinterpret_cast<const float*>(w.ptr);
       g.b_lo_tma = 1;
     }
@@ -896,6 +898,7 @@ extern "C" int krs_gemm_set_workspace(void* dev_buf, size_t bytes) {
   { std::lock_guard<std::mutex> l(krs::g_ws_mu); krs::g_ws_val = krs::Workspace{dev_buf, dev_buf ? bytes : 0, dev}; }
   return KRS_OK;
 }
+extern "C" long long krs_gemm_split_launch_count(void) { return krs::g_split_launches.load(); }
 extern "C" long long krs_gemm_tc_launch_count(void) { return krs::gemm_tc_launches(); }
 extern "C" int krs_gemm_tc_set_trace(void* dev_buf) {
   krs::gemm_tc_set_trace(reinterpret_cast<unsigned long long*>(dev_buf));
