@@ -67,7 +67,7 @@ def run_reference(a):
     if rank != 0:
         return
     from oracle import torch_ref as T
-    cores = os.cpu_count()
+    cores = T.usable_cores()        # min(cpu_count, affinity, cgroup quota): the threads the host really grants
     # a full step of this workload costs ~50 s of CPU time (the dense AdamW sweep over 3.3 GB of tables dominates),
     # so the run is bounded: 1 warm-up step, then timed steps until --cpu-budget-s is spent
     r = T.time_cpu_baseline(B=a.batch, F=a.features, V=a.vocab, E=a.embed_dim, L=a.cross_layers, steps=a.steps,

@@ -97,12 +97,37 @@ def synthetic_c2(F=26, V=1_000_000, E=32, L=3, units=(192, 192), seed=1234):
     return tables, cross, mlp
 
 
+def usable_cores() -> int:
+    """Host threads this process can really run at once: min(cpu_count, scheduler affinity, cgroup CPU quota).  A box
+    that reports 128 CPUs but grants a 16-CPU quota ran the 128-thread baseline 15x slower than 16 threads."""
+    import os
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        pass
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(int(txt[0]) / int(txt[1]) + 0.5)))
+            else:
+                quota = int(txt[0])
+                period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                if quota > 0 and period > 0:
+                    n = min(n, max(1, int(quota / period + 0.5)))
+            break
+        except (OSError, ValueError, IndexError):
+            continue
+    return max(1, n)
+
+
 def time_cpu_baseline(B=65536, F=26, V=1_000_000, E=32, L=3, units=(192, 192), steps=3, warmup=1, optimizer="adamw",
                       threads=None, seed=1234, budget_s=None):
     """examples/s of the CPU restatement on this host.  Returns dict(value, cores, steps, ms_per_step).
     budget_s bounds the wall time: timed steps stop once the budget is spent (at least one is always run)."""
-    import os
-    threads = threads or os.cpu_count()
+    threads = threads or usable_cores()
     torch.set_num_threads(threads)
     tables, cross, mlp = synthetic_c2(F, V, E, L, units, seed)
     model = TorchDCN(tables, cross, mlp, lr=0.01, optimizer=optimizer)
