@@ -7,6 +7,8 @@ from .dot_interaction import DotInteraction
 from .embedding import EmbedReduce, Embedding
 from .feature_cross import FeatureCross
 from .retrieval import BruteForceRetrieval, Retrieval
+from .retrieval_helpers import HardNegativeMining, RemoveAccidentalHits, SamplingProbabilityCorrection
 
 __all__ = ["Layer", "Dense", "Embedding", "EmbedReduce", "DistributedEmbedding", "TableConfig", "FeatureConfig",
-           "FeatureCross", "DotInteraction", "Retrieval", "BruteForceRetrieval", "serialize", "deserialize"]
+           "FeatureCross", "DotInteraction", "Retrieval", "BruteForceRetrieval", "HardNegativeMining", "RemoveAccidentalHits",
+           "SamplingProbabilityCorrection", "serialize", "deserialize"]

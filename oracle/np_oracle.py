@@ -349,6 +349,41 @@ def brute_force_retrieval(q, c, candidate_ids=None, k: int = 10, return_scores: 
 
 
 # --------------------------------------------------------------------------- losses / optimizers
+# ---------------------------------------------------------------------------------------------------------
+# two-tower training helpers (restated for the host-side mirrors in layers/retrieval_helpers.py)
+MAX_FLOAT = float(np.finfo(np.float32).max) / 100.0          # hard_negative_mining.py:9
+SMALLEST_FLOAT = float(np.finfo(np.float32).tiny) / 100.0     # remove_accidental_hits.py:9 (a subnormal)
+
+
+def hard_negative_mining(logits: np.ndarray, labels: np.ndarray, num_hard_negatives: int):
+    """hard_negative_mining.py:70-94: top-(k+1) columns of logits + labels*MAX_FLOAT per row (order unspecified by the
+    reference: sorted=False; here descending), then take_along_axis on logits and labels."""
+    n = logits.shape[-1]
+    num_sampled = min(num_hard_negatives + 1, n)
+    boosted = logits + labels * np.float32(MAX_FLOAT)
+    idx = np.argsort(-boosted, axis=-1, kind="stable")[..., :num_sampled]
+    return np.take_along_axis(logits, idx, axis=-1), np.take_along_axis(labels, idx, axis=-1)
+
+
+def remove_accidental_hits(logits: np.ndarray, labels: np.ndarray, candidate_ids: np.ndarray) -> np.ndarray:
+    """remove_accidental_hits.py:60-97, literally (np.take without an axis = flattened ids, as keras.ops.take)."""
+    if labels.shape != logits.shape:
+        raise ValueError("`labels` and `logits` should have the same shape.")
+    r = candidate_ids.ndim
+    if tuple(labels.shape[labels.ndim - r:]) != tuple(candidate_ids.shape):
+        raise ValueError("`candidate_ids` should have the same shape as the last dimensions of `labels`.")
+    ids = candidate_ids.reshape((1,) * (labels.ndim - r) + candidate_ids.shape)
+    pos = np.expand_dims(np.argmax(labels, axis=-1), -1)
+    pos_ids = np.take(candidate_ids, pos)
+    dup = (pos_ids == ids).astype(labels.dtype) - labels
+    return (logits + dup.astype(logits.dtype) * np.float32(SMALLEST_FLOAT)).astype(logits.dtype)
+
+
+def sampling_probability_correction(logits: np.ndarray, probs: np.ndarray, epsilon: float = 1e-6) -> np.ndarray:
+    """sampling_probability_correction.py:39-58."""
+    return logits - np.log(np.clip(probs.astype(logits.dtype), np.float32(epsilon), np.float32(1.0)))
+
+
 def mse_loss(pred: np.ndarray, label: np.ndarray):
     """keras.losses.MeanSquaredError on (B,1) (examples/dcn.py:128): mean over batch; + dpred."""
     d = pred.reshape(-1) - label.reshape(-1)
