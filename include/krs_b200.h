@@ -179,6 +179,12 @@ int krs_dot_bwd(const float* const* feats, const int64_t* strides, const float* 
  * Q (nq,d), C (nc,d), cand_ids nullable int32 (nc).  top_scores (nq,k) fp32, top_ids (nq,k) int32.
  * workspace: krs_topk_workspace_bytes(). */
 size_t krs_topk_workspace_bytes(int64_t nq, int64_t nc, int d, int k);
+/* Same, with the candidates' low-order TF32 plane C_lo (nullable) precomputed by krs_topk_split_candidates: the tensor-pipe
+ * kernel then streams both planes by TMA and no thread touches a candidate element before the tensor core does. */
+int krs_topk_lo(const float* Q, const float* C, const float* C_lo, const int32_t* cand_ids, float* top_scores,
+                int32_t* top_ids, int64_t nq, int64_t nc, int d, int k, void* workspace, size_t workspace_bytes,
+                void* stream);
+int krs_topk_split_candidates(const float* C, float* C_lo, int64_t nc, int d, void* stream);
 /* Score engine of krs_topk: 0 = auto (tensor pipe when the problem fills the machine and the shape is eligible:
  * d % 4 == 0, d <= 64, k <= 128, nc >= 96), 1 = exact-fp32 FMA score tiles only, 2 = tcgen05 (3xTF32, fp32-level
  * accuracy) whenever eligible.  krs_topk_tc_launch_count() lets tests prove which kernel produced a result. */

@@ -457,6 +457,29 @@ def test_topk_tc_candidate_ids_and_large_slice(K):
         K.ops.set_topk_engine("auto")
 
 
+@pytest.mark.parametrize("nq,nc,d,k", [(260, 100_003, 64, 50), (33, 5000, 32, 100), (129, 3000, 48, 1)])
+def test_topk_tc_with_precomputed_lo_plane(K, nq, nc, d, k):
+    """tensor-pipe path with the candidates' lo plane streamed by TMA (krs_topk_lo): same results as the in-kernel split."""
+    K.ops.set_topk_engine("tcgen05")
+    try:
+        rng = np.random.default_rng(nq + nc)
+        q = rng.normal(size=(nq, d)).astype(np.float32)
+        c = rng.normal(size=(nc, d)).astype(np.float32)
+        tc_, tq = dev(c), dev(q)
+        lo = K.ops.split_candidates_lo(tc_)
+        x = npy(tc_)
+        hi = (x.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+        assert np.abs(npy(lo) - (x - hi)).max() <= np.abs(x - hi).max() * 2.0 ** -10      # lo = tf32_rn(x - trunc_tf32(x))
+        s0, i0 = K.ops.top_k_scores(tq, tc_, None, k)
+        s1, i1 = K.ops.top_k_scores(tq, tc_, None, k, cand_lo=lo)
+        np.testing.assert_array_equal(npy(s0), npy(s1))          # identical arithmetic, only the producer of C_lo differs
+        np.testing.assert_array_equal(npy(i0), npy(i1))
+        ref = q.astype(np.float64) @ c.astype(np.float64).T
+        _check_topk(ref, npy(s1), npy(i1), k)
+    finally:
+        K.ops.set_topk_engine("auto")
+
+
 def test_retrieval_shared_variable_pattern(K):
     # examples/basic_retrieval.py:249-257: assign another layer's embedding variable, then call
     emb = K.layers.Embedding(50, 16)
