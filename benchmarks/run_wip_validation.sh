@@ -8,7 +8,7 @@ echo "tc tests rc=$?"; tail -3 gpurun_out/wip_tc_tests.log
 timeout 420 python -m pytest tests/test_gpu_kernels.py -q -k "topk or brute or retrieval" --timeout 150 -p no:cacheprovider > gpurun_out/wip_topk_tests.log 2>&1
 echo "topk tests rc=$?"; tail -3 gpurun_out/wip_topk_tests.log
 timeout 200 python benchmarks/gemm_probe.py --engines tcgen05,tcgen05_ts > gpurun_out/wip_gemm_probe.log 2>&1; cut -c1-170 gpurun_out/wip_gemm_probe.log
-ENGINE=tcgen05_ts timeout 120 python tests/tc_trace.py > gpurun_out/wip_trace_ts.txt 2>&1
+# (tests/tc_trace.py needs a -DKRS_TC_TRACE=1 build on this branch; skipped here)
 timeout 300 python benchmarks/topk_probe.py --engines tcgen05 > gpurun_out/wip_topk_probe.log 2>&1; cat gpurun_out/wip_topk_probe.log
 timeout 300 python - > gpurun_out/wip_topk_lo_probe.log 2>&1 <<'PY'
 import json, os, sys, torch

@@ -99,7 +99,14 @@ struct TcArgs {
 
 // debug timeline (CTA 0 only): four role-private regions of 2000 (tag, clock64) pairs written with plain
 // stores — a returning atomic would stall the traced thread for ~700 clocks per event and distort the timeline
+// Compiled out unless the library is built with -DKRS_TC_TRACE=1 (KRS_EXTRA_FLAGS=-DKRS_TC_TRACE=1 bash build.sh): even
+// with a null trace pointer the guards (LDC of the pointer, predicate chains, predicated-off address math) were ~17 % of
+// the converter warps' stall samples (ncu source view of the first tcgen05_ts capture).
+#ifndef KRS_TC_TRACE
+#define KRS_TC_TRACE 0
+#endif
 __device__ __forceinline__ void trace_ev(const unsigned long long* tr_c, int role, int& count, unsigned tag, unsigned idx) {
+  if (!KRS_TC_TRACE) return;
   unsigned long long* tr = const_cast<unsigned long long*>(tr_c);
   if (tr == nullptr || blockIdx.x != 0 || count >= 2000) return;
   tr[1 + role * 4000 + 2 * count] = ((unsigned long long)tag << 32) | idx;
@@ -354,9 +361,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const uint32_t d_main = tmem_base + (uint32_t)(acc * 2 * ACC_BN);
       const uint32_t d_small = d_main + (uint32_t)cross_off;
       for (int64_t kb = kb0; kb < kb1; ++kb) {
-        if (g.trace != nullptr && elect_one()) trace_ev(g.trace, 1, tcount, 15, (unsigned)kb);
+        if (KRS_TC_TRACE && g.trace != nullptr && elect_one()) trace_ev(g.trace, 1, tcount, 15, (unsigned)kb);
         mbar_wait_uniform(&conv_bar[stage], phase, g.wait_ns);
-        if (g.trace != nullptr && elect_one()) trace_ev(g.trace, 1, tcount, 16, (unsigned)kb);
+        if (KRS_TC_TRACE && g.trace != nullptr && elect_one()) trace_ev(g.trace, 1, tcount, 16, (unsigned)kb);
         tc_fence_after();
         if (elect_one()) {
           trace_ev(g.trace, 1, tcount, 4, (unsigned)kb);

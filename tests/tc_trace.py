@@ -1,4 +1,5 @@
 """Debug harness: per-role clock64 timeline of CTA 0 of one tcgen05 GEMM (cross forward, C2 shape).
+Needs a trace build of the library: touch keras_rs_b200/csrc/gemm_tc.cu && KRS_EXTRA_FLAGS=-DKRS_TC_TRACE=1 bash keras_rs_b200/csrc/build.sh
 ENGINE=tcgen05|tcgen05_ts  MODE=cross|cross_noh2|cross_x1|dense|sgemm"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
