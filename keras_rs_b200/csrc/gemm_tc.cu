@@ -469,10 +469,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                   if (i < nvb) {
                     const float4 x = bx[j];
                     float4 l;
-                    l.x = tf32_rna_f(x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u));
-                    l.y = tf32_rna_f(x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u));
-                    l.z = tf32_rna_f(x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u));
-                    l.w = tf32_rna_f(x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u));
+                    l.x = tf32_lo_of(x.x);
+                    l.y = tf32_lo_of(x.y);
+                    l.z = tf32_lo_of(x.z);
+                    l.w = tf32_lo_of(x.w);
                     blo[i] = l;
                   }
                 }
@@ -502,7 +502,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               for (int k = 0; k < 16; ++k) {
                 const uint32_t raw = hi[sub][k];
                 const uint32_t h = raw & 0xFFFFE000u;
-                lo[sub][k] = __float_as_uint(tf32_rna_f(__uint_as_float(raw) - __uint_as_float(h)));
+                lo[sub][k] = __float_as_uint(__uint_as_float(raw) - __uint_as_float(h)) + 0x1000u;   // = tf32_lo_of(raw)
                 hi[sub][k] = h;
               }
             mbar_wait(&afree_bar[astage], aphase ^ 1, g.wait_ns);     // MMAs of the stage that used this A stage are done
@@ -558,10 +558,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
             h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
             h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
-            l.x = tf32_rna_f(x.x - h.x);
-            l.y = tf32_rna_f(x.y - h.y);
-            l.z = tf32_rna_f(x.z - h.z);
-            l.w = tf32_rna_f(x.w - h.w);
+            l.x = __uint_as_float(__float_as_uint(x.x - h.x) + 0x1000u);
+            l.y = __uint_as_float(__float_as_uint(x.y - h.y) + 0x1000u);
+            l.z = __uint_as_float(__float_as_uint(x.z - h.z) + 0x1000u);
+            l.w = __uint_as_float(__float_as_uint(x.w - h.w) + 0x1000u);
             if (!g.no_mask) raw[i] = h;
             lo[i < A_VECS ? i + b_vecs : i - A_VECS] = l;      // lo region = B_lo | A_lo
           }
@@ -707,10 +707,10 @@ __global__ void __launch_bounds__(256) split_lo_kernel(const float4* __restrict_
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
     const float4 x = src[i];
     float4 l;
-    l.x = tf32_rna_f(x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u));
-    l.y = tf32_rna_f(x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u));
-    l.z = tf32_rna_f(x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u));
-    l.w = tf32_rna_f(x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u));
+    l.x = tf32_lo_of(x.x);
+    l.y = tf32_lo_of(x.y);
+    l.z = tf32_lo_of(x.z);
+    l.w = tf32_lo_of(x.w);
     dst[i] = l;
   }
 }

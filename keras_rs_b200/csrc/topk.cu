@@ -424,7 +424,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const uint32_t h = hi[i] & 0xFFFFE000u;
-            lo[i] = __float_as_uint(tf32_rna_f(__uint_as_float(hi[i]) - __uint_as_float(h)));
+            lo[i] = __float_as_uint(__uint_as_float(hi[i]) - __uint_as_float(h)) + 0x1000u;       // = tf32_lo_of(raw)
             hi[i] = h;
           }
           // the query columns are still read by the previous item's MMAs until qfree completes
@@ -461,10 +461,10 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
               float4 l;
-              l.x = tf32_rna_f(x[j].x - __uint_as_float(__float_as_uint(x[j].x) & 0xFFFFE000u));
-              l.y = tf32_rna_f(x[j].y - __uint_as_float(__float_as_uint(x[j].y) & 0xFFFFE000u));
-              l.z = tf32_rna_f(x[j].z - __uint_as_float(__float_as_uint(x[j].z) & 0xFFFFE000u));
-              l.w = tf32_rna_f(x[j].w - __uint_as_float(__float_as_uint(x[j].w) & 0xFFFFE000u));
+              l.x = tf32_lo_of(x[j].x);
+              l.y = tf32_lo_of(x[j].y);
+              l.z = tf32_lo_of(x[j].z);
+              l.w = tf32_lo_of(x[j].w);
               lo[gt + j * 128] = l;
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -603,10 +603,10 @@ __global__ void __launch_bounds__(256) topk_split_lo_kernel(const float4* __rest
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
     const float4 x = ldg_nc_f4(reinterpret_cast<const float*>(src + i));
     float4 l;
-    l.x = tf32_rna_f(x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u));
-    l.y = tf32_rna_f(x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u));
-    l.z = tf32_rna_f(x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u));
-    l.w = tf32_rna_f(x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u));
+    l.x = tf32_lo_of(x.x);
+    l.y = tf32_lo_of(x.y);
+    l.z = tf32_lo_of(x.z);
+    l.w = tf32_lo_of(x.w);
     stg_cs_f4(reinterpret_cast<float*>(dst + i), l);
   }
 }
