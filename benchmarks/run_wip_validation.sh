@@ -9,7 +9,9 @@ timeout 420 python -m pytest tests/test_gpu_kernels.py -q -k "topk or brute or r
 echo "topk tests rc=$?"; tail -3 gpurun_out/wip_topk_tests.log
 timeout 200 python benchmarks/gemm_probe.py --engines tcgen05,tcgen05_ts > gpurun_out/wip_gemm_probe.log 2>&1; cut -c1-170 gpurun_out/wip_gemm_probe.log
 # (tests/tc_trace.py needs a -DKRS_TC_TRACE=1 build on this branch; skipped here)
+# tile order: rotated windows (default on this branch) vs plain order (KRS_TOPK_WIN=0)
 timeout 300 python benchmarks/topk_probe.py --engines tcgen05 > gpurun_out/wip_topk_probe.log 2>&1; cat gpurun_out/wip_topk_probe.log
+KRS_TOPK_WIN=0 timeout 300 python benchmarks/topk_probe.py --engines tcgen05 > gpurun_out/wip_topk_probe_win0.log 2>&1; cat gpurun_out/wip_topk_probe_win0.log
 timeout 300 python - > gpurun_out/wip_topk_lo_probe.log 2>&1 <<'PY'
 import json, os, sys, torch
 sys.path.insert(0, os.getcwd())

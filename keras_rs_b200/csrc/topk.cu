@@ -10,6 +10,7 @@
 // (jax.lax.top_k rule adopted in SURVEY.md Appendix A.3), independent of thread scheduling.
 #include <limits.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include <atomic>
 
@@ -258,6 +259,20 @@ __device__ __forceinline__ int score_key(float x) {
 }
 __device__ __forceinline__ float key_score(int key) { return __int_as_float(key >= 0 ? key : (key ^ 0x7fffffff)); }
 
+// Tile order inside a slice.  The q_tiles CTAs that stream the same slice run in near lockstep; in plain order they all
+// ask for the same candidate tile at the same moment, the requests merge into ONE DRAM fetch and EVERY CTA waits out the
+// DRAM latency (ncu: the converters polled the TMA barrier ~70 times per ring entry; 10 ring entries cannot cover it).
+// Windows of `win` tiles are therefore walked with a per-query-tile rotation: each CTA first-touches its own 1/q_tiles of
+// the window and finds the rest already in L2, fetched moments earlier by its neighbours (the window of every concurrently
+// running slice fits in L2).
+__device__ __forceinline__ int64_t slice_tile(int64_t t0, int64_t nt, int64_t j, int win, int qt, int q_tiles) {
+  if (win <= 0) return t0 + j;
+  const int64_t w0 = (j / win) * win;
+  const int64_t wl = imin<int64_t>((int64_t)win, nt - w0);
+  const int64_t r = ((int64_t)qt * wl) / q_tiles;
+  return t0 + w0 + ((j - w0 + r) % wl);
+}
+
 struct TopkTcArgs {
   float* part_s;
   int32_t* part_i;
@@ -267,6 +282,7 @@ struct TopkTcArgs {
   int c_lo_tma;          // the candidates' lo plane is precomputed (krs_topk_split_candidates) and streamed by TMA:
                          // candidate entries skip the converters entirely (TMA -> UMMA)
   int q_tiles;
+  int win;               // rotation window in tiles (0 = plain order)
   int64_t tiles_per_slice, ntiles, n_items;
 };
 
@@ -332,7 +348,8 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         }
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      for (int64_t tile = t0; tile < t1; ++tile)
+      for (int64_t j = 0; j < t1 - t0; ++j) {
+        const int64_t tile = slice_tile(t0, t1 - t0, j, a.win, qt, a.q_tiles);
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait_uniform(&empty_bar[stage], phase ^ 1);
           if (elect_one()) {
@@ -343,6 +360,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+      }
     }
   } else if (warp == 13) {
     // ======================= MMA issuer =======================
@@ -498,7 +516,8 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       float th = -INFINITY;
       const int64_t q_me = (int64_t)qt * TQ + warp * 32 + lane;
       int published = INT_MIN;
-      for (int64_t tile = t0; tile < t1; ++tile) {
+      for (int64_t j = 0; j < t1 - t0; ++j) {
+        const int64_t tile = slice_tile(t0, t1 - t0, j, a.win, qt, a.q_tiles);
         if (q_me < a.nq) th = fmaxf(th, key_score(*reinterpret_cast<volatile int*>(a.g_bound + q_me)));
         mbar_wait_relaxed(&tmem_full[acc], acc_phase);
         tc_fence_after();
@@ -733,6 +752,15 @@ extern "C" int krs_topk_lo(const float* Q, const float* C, const float* C_lo, co
         make_map(&mclo, have_lo ? C_lo : C, nc, d, d, TKB, TNC, CU_TENSOR_MAP_SWIZZLE_64B)) {
       TopkTcArgs t;
       t.c_lo_tma = have_lo ? 1 : 0;
+      {
+        // window ~8 MB of candidate bytes (both planes when the lo plane is streamed): q_tiles CTAs x (SMs / q_tiles)
+        // concurrent slices keep well under the 126 MB L2
+        const int64_t tile_bytes = (int64_t)TNC * d * 4 * (have_lo ? 2 : 1);
+        int64_t win = ((int64_t)8 << 20) / tile_bytes;
+        if (win < 4 * (int64_t)tp.q_tiles) win = 4 * (int64_t)tp.q_tiles;     // at least a few first-touch tiles per CTA
+        t.win = tp.q_tiles > 1 ? (int)imin<int64_t>(win, 1 << 20) : 0;
+        if (const char* e = getenv("KRS_TOPK_WIN")) t.win = atoi(e);
+      }
       t.part_s = reinterpret_cast<float*>(workspace);
       t.part_i = reinterpret_cast<int32_t*>(t.part_s + (size_t)nq * tp.S * k);
       t.g_bound = reinterpret_cast<int*>(t.part_i + (size_t)nq * tp.S * k);
