@@ -274,7 +274,10 @@ def run_ours(a):
 
         if a.optimizer == "adamw":     # dense-exact sweep: p, m, v read + written, g read + re-zeroed
             ms_a = timed(adamw_i, 5, 2) / 5
-            adam_bytes = base.emb.numel() * 4 * 6
+            # rows that ever received a gradient move 24 B per parameter (p, m, v read + written), the others 8 B (p only)
+            ever = getattr(base, "emb_ever", None)
+            hot = 1.0 if ever is None else float(torch.tensor([bin(int(x) & 0xFFFFFFFF).count("1") for x in ever[:65536].tolist()]).sum()) / (65536 * 32.0)
+            adam_bytes = int(base.emb.numel() * 4 * (6 * hot + 2 * (1.0 - hot)))
             kern["adamw_tables"] = {"ms": ms_a, "GBps": adam_bytes / ms_a * 1e-6, "bytes": adam_bytes}
 
         def scatter_i(i):

@@ -213,6 +213,11 @@ int krs_adamw(float* p, float* m, float* v, float* g, uint32_t* touched, int64_t
               float lr, float b1, float b2, float eps, float wd, int64_t step,
               const float* hyper_dev /* nullable device [lr,b1,b2,eps,wd,alpha,step]: overrides the scalars */,
               void* stream);
+/* Same update with an extra persistent bitmap `ever` (one bit per row, zero-initialised by the caller, nullable): rows that
+ * have never received a gradient still hold m = v = 0 exactly, so for them the rule reduces bit for bit to the decoupled
+ * decay of p alone and the sweep moves 8 instead of 24 bytes per parameter; `ever |= touched` is folded in after the sweep. */
+int krs_adamw_cold(float* p, float* m, float* v, float* g, uint32_t* touched, uint32_t* ever, int64_t n, int row_len,
+                   float lr, float b1, float b2, float eps, float wd, int64_t step, const float* hyper_dev, void* stream);
 /* Advances hyper_dev[6] (step) and refreshes hyper_dev[5] (alpha) on the device, so a captured CUDA graph of
  * the training step can be replayed without per-step host parameters. */
 int krs_adam_hyper_advance(float* hyper_dev, void* stream);

@@ -28,10 +28,14 @@ __device__ __forceinline__ void adamw_one(float& p, float& m, float& v, float g,
 }
 
 // One thread per float4.  VEC4 requires n % 4 == 0, row_len % 4 == 0 and 16-byte alignment.
+// `ever` (nullable, arena mode only): one bit per row, set once the row has EVER received a gradient.  A row that never
+// has still holds m = v = 0 exactly, so the full update reduces — bit for bit — to the decoupled decay of p alone
+// (m' = 0, v' = 0, p' = p - p*wd*lr - (0*alpha)/(0+eps)): such rows move 8 instead of 24 bytes per parameter.
 template <bool ARENA>
 __global__ void __launch_bounds__(256) adamw_vec_kernel(float* __restrict__ p, float* __restrict__ m,
                                                         float* __restrict__ v, float* __restrict__ g,
-                                                        const uint32_t* __restrict__ touched, int64_t n4, int row_len4,
+                                                        const uint32_t* __restrict__ touched,
+                                                        const uint32_t* __restrict__ ever, int64_t n4, int row_len4,
                                                         AdamArgs a, const float* __restrict__ hyper) {
   if (hyper) { a.lr = hyper[0]; a.b1 = hyper[1]; a.b2 = hyper[2]; a.eps = hyper[3]; a.wd = hyper[4]; a.alpha = hyper[5]; }
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -42,6 +46,15 @@ __global__ void __launch_bounds__(256) adamw_vec_kernel(float* __restrict__ p, f
     if (ARENA) {
       const int64_t row = i / row_len4;
       hit = (touched[row >> 5] >> (row & 31)) & 1u;
+      if (ever != nullptr && !hit && !((ever[row >> 5] >> (row & 31)) & 1u)) {     // cold row: decay only
+        float4 pc = reinterpret_cast<float4*>(p)[i];
+        pc.x = pc.x - pc.x * a.wd * a.lr;
+        pc.y = pc.y - pc.y * a.wd * a.lr;
+        pc.z = pc.z - pc.z * a.wd * a.lr;
+        pc.w = pc.w - pc.w * a.wd * a.lr;
+        reinterpret_cast<float4*>(p)[i] = pc;
+        continue;
+      }
     }
     float4 gp = make_float4(0.f, 0.f, 0.f, 0.f);
     if (hit) gp = reinterpret_cast<const float4*>(g)[i];
@@ -137,6 +150,17 @@ __global__ void __launch_bounds__(256) dense_sgd_adagrad_kernel(float* __restric
   }
 }
 
+// ever |= touched ; touched = 0   (after the sweep; replaces the memset of the touched bitmap)
+__global__ void __launch_bounds__(256) fold_touched_kernel(uint32_t* __restrict__ ever, uint32_t* __restrict__ touched, int64_t nwords) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t t = touched[i];
+    if (t != 0u) {
+      ever[i] |= t;
+      touched[i] = 0u;
+    }
+  }
+}
+
 // hyper = [lr, b1, b2, eps, wd, alpha, step]: advances the step counter and refreshes the folded bias
 // correction ON THE DEVICE, so a CUDA-graph replay of the training step needs no per-step host parameters.
 __global__ void adam_hyper_advance_kernel(float* hyper) {
@@ -150,9 +174,19 @@ __global__ void adam_hyper_advance_kernel(float* hyper) {
 
 using namespace krs;
 
+extern "C" int krs_adamw_cold(float* p, float* m, float* v, float* g, uint32_t* touched, uint32_t* ever, int64_t n, int row_len,
+                              float lr, float b1, float b2, float eps, float wd, int64_t step, const float* hyper_dev,
+                              void* stream);
 extern "C" int krs_adamw(float* p, float* m, float* v, float* g, uint32_t* touched, int64_t n, int row_len, float lr,
                          float b1, float b2, float eps, float wd, int64_t step, const float* hyper_dev, void* stream) {
+  return krs_adamw_cold(p, m, v, g, touched, nullptr, n, row_len, lr, b1, b2, eps, wd, step, hyper_dev, stream);
+}
+
+extern "C" int krs_adamw_cold(float* p, float* m, float* v, float* g, uint32_t* touched, uint32_t* ever, int64_t n, int row_len,
+                              float lr, float b1, float b2, float eps, float wd, int64_t step, const float* hyper_dev,
+                              void* stream) {
   KRS_REQUIRE(p && m && v && g, "krs_adamw: null argument");
+  KRS_REQUIRE(ever == nullptr || touched != nullptr, "krs_adamw_cold: the ever-touched bitmap needs the gradient arena");
   KRS_REQUIRE(n >= 0 && (step >= 1 || hyper_dev != nullptr), "krs_adamw: bad n/step");
   KRS_REQUIRE(touched == nullptr || (row_len > 0 && n % row_len == 0), "krs_adamw: arena needs n %% row_len == 0");
   if (n == 0) return KRS_OK;
@@ -166,8 +200,8 @@ extern "C" int krs_adamw(float* p, float* m, float* v, float* g, uint32_t* touch
   const int64_t work = vec ? n / 4 : n;
   const unsigned grid = (unsigned)krs::imax<int64_t>(1, krs::imin<int64_t>(ceil_div<int64_t>(work, 256), (int64_t)sm_count() * 32));
   if (vec) {
-    if (touched) adamw_vec_kernel<true><<<grid, 256, 0, s>>>(p, m, v, g, touched, work, row_len / 4, a, hyper_dev);
-    else adamw_vec_kernel<false><<<grid, 256, 0, s>>>(p, m, v, g, nullptr, work, 1, a, hyper_dev);
+    if (touched) adamw_vec_kernel<true><<<grid, 256, 0, s>>>(p, m, v, g, touched, ever, work, row_len / 4, a, hyper_dev);
+    else adamw_vec_kernel<false><<<grid, 256, 0, s>>>(p, m, v, g, nullptr, nullptr, work, 1, a, hyper_dev);
   } else {
     if (touched) adamw_scalar_kernel<true><<<grid, 256, 0, s>>>(p, m, v, g, touched, n, row_len, a, hyper_dev);
     else adamw_scalar_kernel<false><<<grid, 256, 0, s>>>(p, m, v, g, nullptr, n, 1, a, hyper_dev);
@@ -175,7 +209,14 @@ extern "C" int krs_adamw(float* p, float* m, float* v, float* g, uint32_t* touch
   KRS_LAUNCH_CHECK();
   if (touched) {
     const int64_t rows = n / row_len;
-    KRS_CUDA(cudaMemsetAsync(touched, 0, sizeof(uint32_t) * (size_t)ceil_div<int64_t>(rows, 32), s));
+    const int64_t nwords = ceil_div<int64_t>(rows, 32);
+    if (ever != nullptr) {     // (the scalar kernel ignores `ever` and does the full update; the fold keeps it valid)
+      fold_touched_kernel<<<(unsigned)krs::imax<int64_t>(1, krs::imin<int64_t>(ceil_div<int64_t>(nwords, 256), (int64_t)sm_count() * 8)), 256, 0, s>>>(
+          ever, touched, nwords);
+      KRS_LAUNCH_CHECK();
+    } else {
+      KRS_CUDA(cudaMemsetAsync(touched, 0, sizeof(uint32_t) * (size_t)nwords, s));
+    }
   }
   return KRS_OK;
 }

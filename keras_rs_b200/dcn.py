@@ -92,6 +92,9 @@ class DCN(torch.nn.Module):
         self.emb_touched = torch.zeros((self.total_rows // 32,), dtype=torch.int32, device=self.device_)
         self.emb._krs_arena = self.emb_grad
         self.emb._krs_touched = self.emb_touched
+        # rows that have ever received a gradient (AdamW sweeps the others with a decay-only update, krs_adamw_cold)
+        self.emb_ever = torch.zeros_like(self.emb_touched)
+        self.emb._krs_ever = self.emb_ever
 
     # ------------------------------------------------------------------ parameters
     def tables(self):

@@ -535,6 +535,43 @@ def test_adamw_dense_and_arena_match_oracle(K):
         assert float(arena.abs().max()) == 0.0 and int(touched.abs().max()) == 0   # arena re-zeroed
 
 
+def test_adamw_cold_rows_are_bitwise_equal_to_the_dense_update(K):
+    """krs_adamw_cold: rows that never received a gradient get the decay-only update; parameters AND moments must stay
+    bit-identical to the dense rule over several steps, and the ever-touched bitmap must accumulate the touched rows."""
+    rng = np.random.default_rng(53)
+    V, E = 4096, 32
+    p0 = rng.normal(size=(V, E)).astype(np.float32)
+    opt_d, opt_c = K.optimizers.AdamW(learning_rate=0.01), K.optimizers.AdamW(learning_rate=0.01)
+    pd_, pc = dev(p0.copy()), dev(p0.copy())
+    arena = torch.zeros_like(pc)
+    touched = torch.zeros((V // 32,), dtype=torch.int32, device="cuda")
+    ever = torch.zeros_like(touched)
+    pc._krs_arena, pc._krs_touched, pc._krs_ever = arena, touched, ever
+    seen = np.zeros((V,), bool)
+    for step in range(6):
+        rows = rng.choice(V, size=200, replace=False)
+        g = np.zeros_like(p0)
+        g[rows] = rng.normal(size=(200, E)).astype(np.float32)
+        pd_.grad = dev(g)
+        opt_d.apply([pd_])
+        arena.copy_(dev(g))
+        bits = np.zeros((V // 32,), np.uint32)
+        for r in rows:
+            bits[r >> 5] |= np.uint32(1 << (r & 31))
+        touched.copy_(dev(bits.view(np.int32)))
+        opt_c.apply([pc])
+        seen[rows] = True
+        np.testing.assert_array_equal(npy(pc), npy(pd_))
+        for slot in ("m", "v"):
+            np.testing.assert_array_equal(npy(opt_c._state[id(pc)][slot]), npy(opt_d._state[id(pd_)][slot]))
+        got = npy(ever).view(np.uint32)
+        exp = np.zeros((V // 32,), np.uint32)
+        for r in np.nonzero(seen)[0]:
+            exp[r >> 5] |= np.uint32(1 << (r & 31))
+        np.testing.assert_array_equal(got, exp)
+        assert float(arena.abs().max()) == 0.0 and int(touched.abs().max()) == 0
+
+
 @pytest.mark.parametrize("name", ["sgd", "adagrad"])
 def test_sparse_rows_optimizers(K, name):
     rng = np.random.default_rng(52)
