@@ -1,6 +1,7 @@
 #!/bin/bash
 # Branch wip/round2 = main + wip/ksub2 (tcgen05_ts ring stages of 2 x 16 k) + wip/topk-clo (candidate lo plane by TMA)
-# + trace compile-out + one-add lo rounding + rotated top-k windows + krs_adamw_cold (decay-only sweep of never-touched rows).
+# + trace compile-out + one-add lo rounding + rotated top-k windows + krs_adamw_cold (decay-only sweep of never-touched rows)
+# + keras_rs_b200/dlrm.py (ml_perf / C3 model on the public layers, oracle in np_oracle.dlrm_forward/backward).
 # Neither has run on a GPU yet.  Build first (python -c "import __graft_entry__ as g; g.build()"), then:
 #   gpurun --timeout 1500 -- 'bash benchmarks/run_wip_validation.sh'
 mkdir -p gpurun_out
@@ -10,6 +11,8 @@ timeout 420 python -m pytest tests/test_gpu_kernels.py -q -k "topk or brute or r
 echo "topk tests rc=$?"; tail -3 gpurun_out/wip_topk_tests.log
 timeout 300 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_model.py -q -k "adamw or graph or dcn" --timeout 150 -p no:cacheprovider > gpurun_out/wip_adamw_tests.log 2>&1
 echo "adamw/model tests rc=$?"; tail -3 gpurun_out/wip_adamw_tests.log
+timeout 300 python -m pytest tests/test_gpu_zz_dlrm.py -q --timeout 150 -p no:cacheprovider > gpurun_out/wip_dlrm_tests.log 2>&1
+echo "dlrm tests rc=$?"; tail -3 gpurun_out/wip_dlrm_tests.log
 timeout 200 python benchmarks/gemm_probe.py --engines tcgen05,tcgen05_ts > gpurun_out/wip_gemm_probe.log 2>&1; cut -c1-170 gpurun_out/wip_gemm_probe.log
 # (tests/tc_trace.py needs a -DKRS_TC_TRACE=1 build on this branch; skipped here)
 # tile order: rotated windows (default on this branch) vs plain order (KRS_TOPK_WIN=0)
