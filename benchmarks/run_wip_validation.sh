@@ -1,6 +1,7 @@
 #!/bin/bash
 # Branch wip/round2 = main + wip/ksub2 (tcgen05_ts ring stages of 2 x 16 k) + wip/topk-clo (candidate lo plane by TMA)
 # + trace compile-out + one-add lo rounding + rotated top-k windows + krs_adamw_cold (decay-only sweep of never-touched rows)
+# + pipelined AdamW (krs_adamw_rows / krs_adamw_skip, DCN.train_on_batch_pipelined, bench.py --pipeline-adamw)
 # + keras_rs_b200/dlrm.py (ml_perf / C3 model on the public layers, oracle in np_oracle.dlrm_forward/backward).
 # Neither has run on a GPU yet.  Build first (python -c "import __graft_entry__ as g; g.build()"), then:
 #   gpurun --timeout 1500 -- 'bash benchmarks/run_wip_validation.sh'
@@ -35,3 +36,4 @@ print(json.dumps(dict(engine="tcgen05 + precomputed C_lo", ms=round(e0.elapsed_t
 PY
 cat gpurun_out/wip_topk_lo_probe.log
 timeout 300 python bench.py --no-cpu-baseline --steps 10 --warmup 3 > gpurun_out/wip_bench.log 2>&1; tail -1 gpurun_out/wip_bench.log | cut -c1-200
+timeout 300 python bench.py --no-cpu-baseline --steps 20 --warmup 5 --pipeline-adamw > gpurun_out/wip_bench_pipelined.log 2>&1; tail -1 gpurun_out/wip_bench_pipelined.log | cut -c1-200

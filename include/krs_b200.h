@@ -218,6 +218,16 @@ int krs_adamw(float* p, float* m, float* v, float* g, uint32_t* touched, int64_t
  * decay of p alone and the sweep moves 8 instead of 24 bytes per parameter; `ever |= touched` is folded in after the sweep. */
 int krs_adamw_cold(float* p, float* m, float* v, float* g, uint32_t* touched, uint32_t* ever, int64_t n, int row_len,
                    float lr, float b1, float b2, float eps, float wd, int64_t step, const float* hyper_dev, void* stream);
+/* Pipelined step: krs_adamw_rows applies the step's update to the rows the NEXT batch will gather (ids (B,F) int32 with per-feature
+ * row offsets into the arena-wide table; one update per distinct row, its bit set in `pre`), so that the next gather can start;
+ * krs_adamw_skip then sweeps every row whose `skip` (= pre) bit is clear — on any stream, e.g. under the next step's forward and
+ * backward — folds / clears `touched` and clears `skip`.  Together they equal one krs_adamw call, bit for bit. */
+int krs_adamw_rows(float* p, float* m, float* v, float* g, const uint32_t* touched, uint32_t* pre, const int32_t* ids,
+                   const int64_t* row_off, int64_t B, int F, int E, float lr, float b1, float b2, float eps, float wd,
+                   int64_t step, void* stream);
+int krs_adamw_skip(float* p, float* m, float* v, float* g, uint32_t* touched, uint32_t* ever, uint32_t* skip, int64_t n,
+                   int row_len, float lr, float b1, float b2, float eps, float wd, int64_t step, const float* hyper_dev,
+                   void* stream);
 /* Advances hyper_dev[6] (step) and refreshes hyper_dev[5] (alpha) on the device, so a captured CUDA graph of
  * the training step can be replayed without per-step host parameters. */
 int krs_adam_hyper_advance(float* hyper_dev, void* stream);
