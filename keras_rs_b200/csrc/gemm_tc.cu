@@ -1,6 +1,6 @@
 // gemm_tc.cu — tcgen05 (5th-gen tensor core) GEMM with fp32-level accuracy via a 3-term TF32 split.
 //
-// "Engine 1" of krs::gemm: the dense contractions of FeatureCross / Dense and their backward passes
+// Engines 1 and 2 of krs::gemm: the dense contractions of FeatureCross / Dense and their backward passes
 // (W·x_i, dz·V^T, x^T·dz) on the tensor pipe, with the same fused epilogues as gemm_ffma.cu
 // (+bias, pre_activation, +diag·x, x0 ⊙ (·) + x kept in registers).
 //
@@ -9,28 +9,35 @@
 // (the dropped lo·lo term is ~2^-22 relative), which keeps results within ~1e-6 of an fp32 matmul —
 // inside the 1e-5 bar of the north star, which a single-pass TF32 product (1e-3) would miss.
 //
-// Structure (one CTA per SM, persistent over output tiles, 448 threads):
-//   warp 0      TMA producer: cp.async.bulk.tensor fp32 tiles global -> shared (mbarrier complete_tx)
-//   warp 1      MMA issuer: one elected lane issues tcgen05.mma.kind::tf32 (SS operands, D in TMEM),
-//               tcgen05.commit releases shared-memory stages / publishes the accumulator
-//   warps 2-5   epilogue: tcgen05.ld accumulator rows -> registers -> fused epilogue -> global
-//   warps 6-13  converters: shared -> registers -> shared, write hi (in place) and lo tiles (highest
-//               warp ids: the scheduler arbitrates highest-warp-id first and they are the critical stage)
-// Shared memory ring: 4 stages x (A_raw | B_raw | A_lo | B_lo), BK = 16 floats per stage.
-// TMEM: 512 columns = 2 stages x TWO accumulators x 128 columns (128 lanes = the 128 rows of the tile), so the
-// epilogue of tile i overlaps the mainloop of tile i+1.  Within a stage the hi·hi
-// products and the small cross terms (lo·hi + hi·lo) accumulate separately and are added in fp32
-// registers by the epilogue.  Reason (measured, tests/test_gpu_tc.py): the tensor core's fp32
-// accumulate truncates, so the error grows with the number of accumulations into one TMEM tile
-// (~0.5 * 6e-8 per step, systematic).  Keeping the small terms out of the main accumulator cuts the
-// step count 3x; long reductions (the batch-dimension weight gradients) are additionally split so
-// that no accumulator sees more than KC_MAX/8 steps, partial tiles being combined with fp32 RED
-// (round-to-nearest) in global memory.
+// Structure (one CTA per SM, persistent over output tiles, 512 threads = 4 warpgroups re-budgeted with setmaxnreg):
+//   warps 0-3    epilogue: tcgen05.ld accumulator rows -> registers -> shared-memory transpose -> fused epilogue -> global,
+//                instantiated per (kind, activation class) so the per-float4 code is straight-line
+//   warps 4-11   converters.  VER 1 (engine "tcgen05"): shared -> registers -> shared, write the A_lo / B_lo tiles.
+//                VER 2 (engine "tcgen05_ts", the default): two groups of 4 warps take alternate k-blocks; a thread owns one
+//                tile row, splits its 16 raw floats in registers and parks hi / lo in a 4-deep TENSOR-MEMORY ring with
+//                tcgen05.st, so the A operand never crosses the shared-memory port again (TS-form MMAs)
+//   warp 12      TMA producer: cp.async.bulk.tensor fp32 tiles global -> shared (mbarrier complete_tx); also streams the
+//                precomputed B_lo plane of weight operands (split_lo_kernel + krs_gemm_set_workspace)
+//   warp 13      MMA issuer: tcgen05.mma.kind::tf32 from ONE elect.sync lane of a provably uniform warp (the warp index
+//                comes from a shuffle broadcast), descriptors in uniform registers; per k-step  A_hi x [B_hi | B_lo] as one
+//                N = 2*bn instruction ([main | cross] accumulators are adjacent) and  A_lo x B_hi  into the cross accumulator;
+//                tcgen05.commit releases ring stages / A stages / publishes the accumulators
+//   warps 14-15  idle (they complete the warpgroup)
+// Shared memory ring (depth chosen per launch, 10 at bn = 96): VER 2  A_raw | B_raw | B_lo ; VER 1  A_raw | B_raw | B_lo | A_lo,
+// BK = 16 floats per stage.
+// TMEM: 2 accumulator stages x (main | cross) x bn columns (bn <= 128 in VER 1, <= 96 in VER 2 whose columns 384..511 hold the
+// A ring), 128 lanes = the 128 rows of the tile, so the epilogue of tile i overlaps the mainloop of tile i+1.  The hi*hi
+// products and the small cross terms (lo*hi + hi*lo) accumulate separately and are added in fp32 registers by the
+// epilogue.  Reason (measured, tests/test_gpu_tc.py): the tensor core's fp32 accumulate truncates, so the error grows with
+// the number of accumulations into one TMEM tile (~0.5 * 6e-8 per step, systematic).  Keeping the small terms out of the
+// main accumulator cuts the step count 3x; long reductions (the batch-dimension weight gradients) are additionally split
+// so that no accumulator sees more than KC_MAX/8 steps, partial tiles being combined with fp32 RED (round-to-nearest) in
+// global memory.  What the measurements changed, step by step: DESIGN.md section 4.1.
 //
 // Operand layouts: K-contiguous operands use 64-byte rows with SWIZZLE_64B (K-major UMMA
 // descriptors), MN-contiguous operands (x^T, dz in the weight-gradient GEMM, V in the forward) use
-// 32-element x 16-row boxes with SWIZZLE_128B (MN-major descriptors).  Ragged edges are handled by
-// TMA out-of-bounds zero fill on loads and guards on stores.
+// 32-element x 16-row boxes with SWIZZLE_128B_BASE32B (MN-major descriptors; unswizzled for the A operand of VER 2, which only
+// converter threads read).  Ragged edges are handled by TMA out-of-bounds zero fill on loads and guards on stores.
 #include <cuda.h>
 #include <cudaTypedefs.h>
 

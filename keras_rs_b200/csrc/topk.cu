@@ -2,10 +2,15 @@
 //
 // Replaces Retrieval.compute_score (retrieval.py:101-117: matmul(q, transpose(c))) followed by
 // keras.ops.top_k and the optional ops.take(candidate_ids, top_ids) (brute_force_retrieval.py:139-143).
-// The (nq, nc) score matrix (164 GB at C4) is never materialised: each CTA owns a 64-query tile and a
-// slice of the candidates, computes 64x128 score tiles in registers (exact fp32 FMA), filters them
-// against the running k-th best score of each query and merges the few survivors into per-query
-// sorted lists held in shared memory.  A second kernel merges the per-slice lists.
+// The (nq, nc) score matrix (164 GB at C4) is never materialised.  Two score engines share the selection rule and the
+// merge kernel:
+//   * topk_tc_kernel (tensor pipe, the default for large problems; see the block comment above it): tcgen05 3xTF32 score
+//     tiles with the 128-query tile parked in tensor memory, 41 ms at C4;
+//   * topk_partial_kernel (exact-fp32 FMA; small problems and shapes the tensor-pipe kernel does not take: d % 4 != 0,
+//     d > 64): each CTA owns a 64-query tile and a slice of the candidates, computes 64x128 score tiles in registers,
+//     filters them against the running k-th best score of each query and merges the few survivors into per-query
+//     sorted lists held in shared memory, 257 ms at C4.
+// topk_merge_kernel then merges the per-slice lists of every query.
 // Ordering is total and deterministic: score descending, ties -> lowest candidate index first
 // (jax.lax.top_k rule adopted in SURVEY.md Appendix A.3), independent of thread scheduling.
 #include <limits.h>
