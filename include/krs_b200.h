@@ -179,6 +179,12 @@ int krs_dot_bwd(const float* const* feats, const int64_t* strides, const float* 
  * Q (nq,d), C (nc,d), cand_ids nullable int32 (nc).  top_scores (nq,k) fp32, top_ids (nq,k) int32.
  * workspace: krs_topk_workspace_bytes(). */
 size_t krs_topk_workspace_bytes(int64_t nq, int64_t nc, int d, int k);
+/* Same, with the candidates' low-order TF32 plane C_lo (nullable) precomputed by krs_topk_split_candidates: the tensor-pipe
+ * kernel then streams both planes by TMA and no thread touches a candidate element before the tensor core does. */
+int krs_topk_lo(const float* Q, const float* C, const float* C_lo, const int32_t* cand_ids, float* top_scores,
+                int32_t* top_ids, int64_t nq, int64_t nc, int d, int k, void* workspace, size_t workspace_bytes,
+                void* stream);
+int krs_topk_split_candidates(const float* C, float* C_lo, int64_t nc, int d, void* stream);
 /* Score engine of krs_topk: 0 = auto (tensor pipe when the problem fills the machine and the shape is eligible:
  * d % 4 == 0, d <= 64, k <= 128, nc >= 96), 1 = exact-fp32 FMA score tiles only, 2 = tcgen05 (3xTF32, fp32-level
  * accuracy) whenever eligible.  krs_topk_tc_launch_count() lets tests prove which kernel produced a result. */
@@ -207,6 +213,21 @@ int krs_adamw(float* p, float* m, float* v, float* g, uint32_t* touched, int64_t
               float lr, float b1, float b2, float eps, float wd, int64_t step,
               const float* hyper_dev /* nullable device [lr,b1,b2,eps,wd,alpha,step]: overrides the scalars */,
               void* stream);
+/* Same update with an extra persistent bitmap `ever` (one bit per row, zero-initialised by the caller, nullable): rows that
+ * have never received a gradient still hold m = v = 0 exactly, so for them the rule reduces bit for bit to the decoupled
+ * decay of p alone and the sweep moves 8 instead of 24 bytes per parameter; `ever |= touched` is folded in after the sweep. */
+int krs_adamw_cold(float* p, float* m, float* v, float* g, uint32_t* touched, uint32_t* ever, int64_t n, int row_len,
+                   float lr, float b1, float b2, float eps, float wd, int64_t step, const float* hyper_dev, void* stream);
+/* Pipelined step: krs_adamw_rows applies the step's update to the rows the NEXT batch will gather (ids (B,F) int32 with per-feature
+ * row offsets into the arena-wide table; one update per distinct row, its bit set in `pre`), so that the next gather can start;
+ * krs_adamw_skip then sweeps every row whose `skip` (= pre) bit is clear — on any stream, e.g. under the next step's forward and
+ * backward — folds / clears `touched` and clears `skip`.  Together they equal one krs_adamw call, bit for bit. */
+int krs_adamw_rows(float* p, float* m, float* v, float* g, const uint32_t* touched, uint32_t* pre, const int32_t* ids,
+                   const int64_t* row_off, int64_t B, int F, int E, float lr, float b1, float b2, float eps, float wd,
+                   int64_t step, void* stream);
+int krs_adamw_skip(float* p, float* m, float* v, float* g, uint32_t* touched, uint32_t* ever, uint32_t* skip, int64_t n,
+                   int row_len, float lr, float b1, float b2, float eps, float wd, int64_t step, const float* hyper_dev,
+                   void* stream);
 /* Advances hyper_dev[6] (step) and refreshes hyper_dev[5] (alpha) on the device, so a captured CUDA graph of
  * the training step can be replayed without per-step host parameters. */
 int krs_adam_hyper_advance(float* hyper_dev, void* stream);

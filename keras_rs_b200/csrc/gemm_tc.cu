@@ -73,7 +73,9 @@ constexpr int KC_MAX = 1024;                     // max K elements accumulated i
 template <int VER> struct Cfg {
   static constexpr int ACC_BN = VER == 2 ? 96 : 128;   // max N tile == accumulator width
   static constexpr int A_COL0 = 4 * ACC_BN;            // VER 2: first TMEM column of the A ring
-  static constexpr int SA = 4;                         // VER 2: A ring depth (32 columns each: hi | lo)
+  static constexpr int KSUB = VER == 2 ? 2 : 1;        // 16-wide k sub-blocks per ring stage: VER 2 moves 32 k per barrier
+                                                       // round trip (the converter chain is latency-bound)
+  static constexpr int SA = 4 / KSUB;                  // VER 2: A ring depth (KSUB x 32 columns each: hi | lo per sub-block)
 };
 
 std::atomic<long long> g_tc_launches{0};
@@ -104,7 +106,14 @@ struct TcArgs {
 
 // debug timeline (CTA 0 only): four role-private regions of 2000 (tag, clock64) pairs written with plain
 // stores — a returning atomic would stall the traced thread for ~700 clocks per event and distort the timeline
+// Compiled out unless the library is built with -DKRS_TC_TRACE=1 (KRS_EXTRA_FLAGS=-DKRS_TC_TRACE=1 bash build.sh): even
+// with a null trace pointer the guards (LDC of the pointer, predicate chains, predicated-off address math) were ~17 % of
+// the converter warps' stall samples (ncu source view of the first tcgen05_ts capture).
+#ifndef KRS_TC_TRACE
+#define KRS_TC_TRACE 0
+#endif
 __device__ __forceinline__ void trace_ev(const unsigned long long* tr_c, int role, int& count, unsigned tag, unsigned idx) {
+  if (!KRS_TC_TRACE) return;
   unsigned long long* tr = const_cast<unsigned long long*>(tr_c);
   if (tr == nullptr || blockIdx.x != 0 || count >= 2000) return;
   tr[1 + role * 4000 + 2 * count] = ((unsigned long long)tag << 32) | idx;
@@ -221,6 +230,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                const __grid_constant__ CUtensorMap tmap_blo, const TcArgs g) {
   constexpr int ACC_BN = Cfg<VER>::ACC_BN;
   constexpr int SA = Cfg<VER>::SA;
+  constexpr int KSUB = Cfg<VER>::KSUB;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // carve: stages first (1024-aligned), then barriers
   // align by OFFSET (not by integer round trip) so the compiler keeps the shared address space (LDS/STS,
@@ -228,7 +238,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int b_bytes = g.bn * BK * 4;
   const int raw_bytes = A_BYTES + b_bytes;
-  const int stage_bytes = VER == 2 ? raw_bytes + b_bytes : 2 * raw_bytes;   // A_raw | B_raw | B_lo (| A_lo in VER 1)
+  const int sub_bytes = VER == 2 ? raw_bytes + b_bytes : 2 * raw_bytes;     // one 16-k sub-block: A_raw | B_raw | B_lo (| A_lo in VER 1)
+  const int stage_bytes = KSUB * sub_bytes;
   const int blo_off = raw_bytes;               // B_lo directly after B_raw: [B_hi | B_lo] is one 2*bn-row operand (fuse_n)
   const int alo_off = raw_bytes + b_bytes;     // VER 1 only
   const int cross_off = g.bn;                  // cross-term accumulator = main + bn columns
@@ -279,7 +290,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   // register budget per role (warpgroup granular; 512 threads start at 128 registers each): the epilogue needs
   // room for a chunk of operand prefetches, converters / TMA / MMA need little.  Each role's branch begins with
   // its own setmaxnreg so that ptxas allocates that branch against the adjusted budget.
-  if (warp >= 12) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(56));
+  if (warp >= 12) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(VER == 2 ? 72 : 56));
   if (warp == W_TMA) {
     // ======================= TMA producer =======================
     // every lane waits for the free stage; lane 0 arms the transaction count, then the boxes of the stage
@@ -300,10 +311,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         // the stage with warp-uniform coordinates (UTMALDG takes uniform registers: per-lane boxes were compiled
         // into R2UR + ELECT / BRA.U.ANY waterfall loops)
         mbar_wait_uniform(&empty_bar[stage], phase ^ 1, g.wait_ns);
-        unsigned char* st = smem + (size_t)stage * stage_bytes;
-        const int k0 = (int)(kb * BK);
         if (elect_one()) {
-          mbar_expect_tx(&full_bar[stage], (uint32_t)(raw_bytes + (g.b_lo_tma ? b_bytes : 0)));
+          mbar_expect_tx(&full_bar[stage], (uint32_t)(KSUB * (raw_bytes + (g.b_lo_tma ? b_bytes : 0))));
+#pragma unroll
+          for (int sub = 0; sub < KSUB; ++sub) {
+          unsigned char* st = smem + (size_t)stage * stage_bytes + (size_t)sub * sub_bytes;
+          const int k0 = (int)(kb * (BK * KSUB)) + sub * BK;
           if (!g.a_mn_major) tma_load_2d(st, &tmap_a, k0, tm * BM, &full_bar[stage]);                       // box {16 k, 128 m}
           else if (g.a_3d) tma_load_3d(st, &tmap_a, 0, k0, tm * (BM / 32), &full_bar[stage]);              // box {32 m, 16 k, 4}
           else
@@ -319,6 +332,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             else if (g.b_3d) tma_load_3d(sl, &tmap_blo, 0, k0, tn * (g.bn / 32), &full_bar[stage]);
             else
               for (int i = 0; i < nB; ++i) tma_load_2d(sl + i * 2048, &tmap_blo, tn * g.bn + i * 32, k0, &full_bar[stage]);
+          }
           }
           trace_ev(g.trace, 0, tcount, 1, (unsigned)kb);
         }
@@ -354,9 +368,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const uint32_t d_main = tmem_base + (uint32_t)(acc * 2 * ACC_BN);
       const uint32_t d_small = d_main + (uint32_t)cross_off;
       for (int64_t kb = kb0; kb < kb1; ++kb) {
-        if (g.trace != nullptr && elect_one()) trace_ev(g.trace, 1, tcount, 15, (unsigned)kb);
+        if (KRS_TC_TRACE && g.trace != nullptr && elect_one()) trace_ev(g.trace, 1, tcount, 15, (unsigned)kb);
         mbar_wait_uniform(&conv_bar[stage], phase, g.wait_ns);
-        if (g.trace != nullptr && elect_one()) trace_ev(g.trace, 1, tcount, 16, (unsigned)kb);
+        if (KRS_TC_TRACE && g.trace != nullptr && elect_one()) trace_ev(g.trace, 1, tcount, 16, (unsigned)kb);
         tc_fence_after();
         if (elect_one()) {
           trace_ev(g.trace, 1, tcount, 4, (unsigned)kb);
@@ -364,13 +378,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           // 14-bit start-address field: one 32-bit add each instead of rebuilding the bit fields
           const uint32_t so = (uint32_t)(stage * stage_bytes) >> 4;
           if constexpr (VER == 2) {
-            const uint32_t ta_hi = tmem_base + (uint32_t)(Cfg<VER>::A_COL0 + astage * 32);   // lanes 0..127
-            const uint32_t ta_lo = ta_hi + 16;
 #pragma unroll
-            for (int ks = 0; ks < BK / 8; ++ks) {
-              const uint64_t dbh = dB_hi + so + (ks ? b_kstep16 : 0u);
-              const uint64_t dbl = dB_lo + so + (ks ? b_kstep16 : 0u);
-              const uint32_t first = (kb == kb0 && ks == 0) ? 0u : 1u;
+            for (int sk = 0; sk < KSUB * (BK / 8); ++sk) {
+              const int sub = sk / (BK / 8), ks = sk % (BK / 8);
+              const uint32_t ta_hi = tmem_base + (uint32_t)(Cfg<VER>::A_COL0 + astage * (32 * KSUB) + sub * 32);   // lanes 0..127
+              const uint32_t ta_lo = ta_hi + 16;
+              const uint32_t sso = so + ((uint32_t)(sub * sub_bytes) >> 4);
+              const uint64_t dbh = dB_hi + sso + (ks ? b_kstep16 : 0u);
+              const uint64_t dbl = dB_lo + sso + (ks ? b_kstep16 : 0u);
+              const uint32_t first = (kb == kb0 && sk == 0) ? 0u : 1u;
               if (g.fuse_n) {
                 // B_lo follows B_hi in the stage: one N = 2*bn MMA yields [hi*hi | hi*lo] in [d_main, d_main + 2*bn)
                 tc_mma_tf32_ts(d_main, ta_hi + 8 * ks, dbh, idesc_ts2, first);
@@ -441,52 +457,69 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           if ((int)(cnt & 1u) == grp) {
             mbar_wait(&full_bar[stage], phase, g.wait_ns);
             if (ct == 0) trace_ev(g.trace, 2, tcount, 2, (unsigned)kb);
-            const unsigned char* st = smem + (size_t)stage * stage_bytes;
-            uint32_t a[16];
-            if (!g.a_mn_major) {
+            const unsigned char* st0 = smem + (size_t)stage * stage_bytes;
+            // B tiles first (only when the lo plane is not streamed by TMA): short-lived registers
+            if (nvb > 0) {
 #pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                const uint4 v = *reinterpret_cast<const uint4*>(st + a_row_off + ((((uint32_t)c) ^ a_sw) << 4));
-                a[4 * c + 0] = v.x; a[4 * c + 1] = v.y; a[4 * c + 2] = v.z; a[4 * c + 3] = v.w;
+              for (int sub = 0; sub < KSUB; ++sub) {
+                const float4* braw = reinterpret_cast<const float4*>(st0 + (size_t)sub * sub_bytes + A_BYTES);
+                float4* blo = reinterpret_cast<float4*>(smem + (size_t)stage * stage_bytes + (size_t)sub * sub_bytes + blo_off);
+                float4 bx[MAXVB];
+#pragma unroll
+                for (int j = 0; j < MAXVB; ++j) {
+                  const int i = gt + j * 128;
+                  if (i < nvb) bx[j] = braw[i];
+                }
+#pragma unroll
+                for (int j = 0; j < MAXVB; ++j) {
+                  const int i = gt + j * 128;
+                  if (i < nvb) {
+                    const float4 x = bx[j];
+                    float4 l;
+                    l.x = tf32_lo_of(x.x);
+                    l.y = tf32_lo_of(x.y);
+                    l.z = tf32_lo_of(x.z);
+                    l.w = tf32_lo_of(x.w);
+                    blo[i] = l;
+                  }
+                }
               }
-            } else {
-              // MN-major raw tile, unswizzled: 4 blocks of [16 k rows x 32 m]; lanes read consecutive words
-#pragma unroll
-              for (int k = 0; k < 16; ++k)
-                a[k] = *reinterpret_cast<const uint32_t*>(st + q * 2048 + k * 128 + lane * 4);
             }
-            const float4* braw = reinterpret_cast<const float4*>(st + A_BYTES);
-            float4* blo = reinterpret_cast<float4*>(smem + (size_t)stage * stage_bytes + blo_off);
-            float4 bx[MAXVB];
+            // A rows of every sub-block: all loads, then the splits, then ONE wait for the TMEM stage
+            uint32_t hi[KSUB][16], lo[KSUB][16];
 #pragma unroll
-            for (int j = 0; j < MAXVB; ++j) {
-              const int i = gt + j * 128;
-              if (i < nvb) bx[j] = braw[i];
-            }
-            uint32_t hi[16], lo[16];
+            for (int sub = 0; sub < KSUB; ++sub) {
+              const unsigned char* st = st0 + (size_t)sub * sub_bytes;
+              if (!g.a_mn_major) {
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-              hi[k] = a[k] & 0xFFFFE000u;
-              lo[k] = __float_as_uint(tf32_rna_f(__uint_as_float(a[k]) - __uint_as_float(hi[k])));
+                for (int c = 0; c < 4; ++c) {
+                  const uint4 v = *reinterpret_cast<const uint4*>(st + a_row_off + ((((uint32_t)c) ^ a_sw) << 4));
+                  hi[sub][4 * c + 0] = v.x; hi[sub][4 * c + 1] = v.y; hi[sub][4 * c + 2] = v.z; hi[sub][4 * c + 3] = v.w;
+                }
+              } else {
+                // MN-major raw tile, unswizzled: 4 blocks of [16 k rows x 32 m]; lanes read consecutive words
+#pragma unroll
+                for (int k = 0; k < 16; ++k)
+                  hi[sub][k] = *reinterpret_cast<const uint32_t*>(st + q * 2048 + k * 128 + lane * 4);
+              }
             }
-            mbar_wait(&afree_bar[astage], aphase ^ 1, g.wait_ns);     // MMAs of the k-block that used this A stage are done
+#pragma unroll
+            for (int sub = 0; sub < KSUB; ++sub)
+#pragma unroll
+              for (int k = 0; k < 16; ++k) {
+                const uint32_t raw = hi[sub][k];
+                const uint32_t h = raw & 0xFFFFE000u;
+                lo[sub][k] = __float_as_uint(__uint_as_float(raw) - __uint_as_float(h)) + 0x1000u;   // = tf32_lo_of(raw)
+                hi[sub][k] = h;
+              }
+            mbar_wait(&afree_bar[astage], aphase ^ 1, g.wait_ns);     // MMAs of the stage that used this A stage are done
             tc_fence_after();
             if (ct == 0) trace_ev(g.trace, 2, tcount, 9, (unsigned)kb);
-            const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(Cfg<VER>::A_COL0 + astage * 32);
-            tc_st16(ta, hi);
-            tc_st16(ta + 16, lo);
+            const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(Cfg<VER>::A_COL0 + astage * (32 * KSUB));
 #pragma unroll
-            for (int j = 0; j < MAXVB; ++j) {
-              const int i = gt + j * 128;
-              if (i < nvb) {
-                const float4 x = bx[j];
-                float4 l;
-                l.x = tf32_rna_f(x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u));
-                l.y = tf32_rna_f(x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u));
-                l.z = tf32_rna_f(x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u));
-                l.w = tf32_rna_f(x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u));
-                blo[i] = l;
-              }
+            for (int sub = 0; sub < KSUB; ++sub) {
+              tc_st16(ta + (uint32_t)(sub * 32), hi[sub]);
+              tc_st16(ta + (uint32_t)(sub * 32 + 16), lo[sub]);
             }
             if (ct == 0) trace_ev(g.trace, 2, tcount, 8, (unsigned)kb);
             tc_wait_st();                                                     // TMEM stores complete
@@ -532,10 +565,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
             h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
             h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
-            l.x = tf32_rna_f(x.x - h.x);
-            l.y = tf32_rna_f(x.y - h.y);
-            l.z = tf32_rna_f(x.z - h.z);
-            l.w = tf32_rna_f(x.w - h.w);
+            l.x = __uint_as_float(__float_as_uint(x.x - h.x) + 0x1000u);
+            l.y = __uint_as_float(__float_as_uint(x.y - h.y) + 0x1000u);
+            l.z = __uint_as_float(__float_as_uint(x.z - h.z) + 0x1000u);
+            l.w = __uint_as_float(__float_as_uint(x.w - h.w) + 0x1000u);
             if (!g.no_mask) raw[i] = h;
             lo[i < A_VECS ? i + b_vecs : i - A_VECS] = l;      // lo region = B_lo | A_lo
           }
@@ -681,10 +714,10 @@ __global__ void __launch_bounds__(256) split_lo_kernel(const float4* __restrict_
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
     const float4 x = src[i];
     float4 l;
-    l.x = tf32_rna_f(x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u));
-    l.y = tf32_rna_f(x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u));
-    l.z = tf32_rna_f(x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u));
-    l.w = tf32_rna_f(x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u));
+    l.x = tf32_lo_of(x.x);
+    l.y = tf32_lo_of(x.y);
+    l.z = tf32_lo_of(x.z);
+    l.w = tf32_lo_of(x.w);
     dst[i] = l;
   }
 }
@@ -767,7 +800,8 @@ int gemm_tc(const float* A, int64_t lda, bool transA, const float* B, int64_t ld
   g.bn = pick_bn(N, g.b_mn_major != 0, ver == 2 ? Cfg<2>::ACC_BN : Cfg<1>::ACC_BN);
   g.tiles_m = (int)ceil_div<int64_t>(M, BM);
   g.tiles_n = (int)ceil_div<int64_t>(N, g.bn);
-  g.kblocks_total = ceil_div<int64_t>(K, BK);
+  const int ksub = ver == 2 ? Cfg<2>::KSUB : Cfg<1>::KSUB;
+  g.kblocks_total = ceil_div<int64_t>(K, BK * ksub);          // ring stages along K (KSUB sub-blocks of 16 each)
   g.kblocks_per_split = ceil_div<int64_t>(g.kblocks_total, split_k);
   g.splits = (int)ceil_div<int64_t>(g.kblocks_total, g.kblocks_per_split);
   g.atomic_out = g.splits > 1 ? 1 : 0;
@@ -850,7 +884,7 @@ int gemm_tc(const float* A, int64_t lda, bool transA, const float* B, int64_t ld
   if (g.atomic_out && !accumulate)
     KRS_CUDA(cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, stream));
 
-  const size_t stage_bytes = ver == 2 ? (size_t)(A_BYTES + 2 * g.bn * BK * 4) : 2 * (size_t)(A_BYTES + g.bn * BK * 4);
+  const size_t stage_bytes = ver == 2 ? (size_t)ksub * (size_t)(A_BYTES + 2 * g.bn * BK * 4) : 2 * (size_t)(A_BYTES + g.bn * BK * 4);
   const size_t budget = 227 * 1024 - 1024 - 512 - EPI_SMEM_BYTES;   // alignment slack + barriers + epilogue staging
   g.stages = (int)imin<int64_t>(MAX_STAGES, (int64_t)(budget / stage_bytes));
   if (g.stages < 3) return KRS_EUNSUPPORTED;

@@ -28,10 +28,15 @@ __device__ __forceinline__ void adamw_one(float& p, float& m, float& v, float g,
 }
 
 // One thread per float4.  VEC4 requires n % 4 == 0, row_len % 4 == 0 and 16-byte alignment.
+// `ever` (nullable, arena mode only): one bit per row, set once the row has EVER received a gradient.  A row that never
+// has still holds m = v = 0 exactly, so the full update reduces — bit for bit — to the decoupled decay of p alone
+// (m' = 0, v' = 0, p' = p - p*wd*lr - (0*alpha)/(0+eps)): such rows move 8 instead of 24 bytes per parameter.
 template <bool ARENA>
 __global__ void __launch_bounds__(256) adamw_vec_kernel(float* __restrict__ p, float* __restrict__ m,
                                                         float* __restrict__ v, float* __restrict__ g,
-                                                        const uint32_t* __restrict__ touched, int64_t n4, int row_len4,
+                                                        const uint32_t* __restrict__ touched,
+                                                        const uint32_t* __restrict__ ever,
+                                                        const uint32_t* __restrict__ skip, int64_t n4, int row_len4,
                                                         AdamArgs a, const float* __restrict__ hyper) {
   if (hyper) { a.lr = hyper[0]; a.b1 = hyper[1]; a.b2 = hyper[2]; a.eps = hyper[3]; a.wd = hyper[4]; a.alpha = hyper[5]; }
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -41,7 +46,17 @@ __global__ void __launch_bounds__(256) adamw_vec_kernel(float* __restrict__ p, f
     bool hit = !ARENA;
     if (ARENA) {
       const int64_t row = i / row_len4;
+      if (skip != nullptr && ((skip[row >> 5] >> (row & 31)) & 1u)) continue;     // already updated by krs_adamw_rows
       hit = (touched[row >> 5] >> (row & 31)) & 1u;
+      if (ever != nullptr && !hit && !((ever[row >> 5] >> (row & 31)) & 1u)) {     // cold row: decay only
+        float4 pc = reinterpret_cast<float4*>(p)[i];
+        pc.x = pc.x - pc.x * a.wd * a.lr;
+        pc.y = pc.y - pc.y * a.wd * a.lr;
+        pc.z = pc.z - pc.z * a.wd * a.lr;
+        pc.w = pc.w - pc.w * a.wd * a.lr;
+        reinterpret_cast<float4*>(p)[i] = pc;
+        continue;
+      }
     }
     float4 gp = make_float4(0.f, 0.f, 0.f, 0.f);
     if (hit) gp = reinterpret_cast<const float4*>(g)[i];
@@ -137,6 +152,49 @@ __global__ void __launch_bounds__(256) dense_sgd_adagrad_kernel(float* __restric
   }
 }
 
+// Hot rows of a pipelined AdamW step: the rows the NEXT batch will gather get their update first (one warp per lookup;
+// the lane that flips the row's bit in `pre` owns the row, duplicates skip), the rest of the table is swept later by
+// adamw_vec_kernel with skip = pre, possibly on another stream under the next step's forward / backward.
+struct RowOffsets { int64_t off[64]; };
+__global__ void __launch_bounds__(256) adamw_rows_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
+                                                         float* __restrict__ g, const uint32_t* __restrict__ touched,
+                                                         uint32_t* __restrict__ pre, const int32_t* __restrict__ ids,
+                                                         const RowOffsets ro, int64_t n_lookups, int F, int E, AdamArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t idx = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; idx < n_lookups; idx += nwarps) {
+    const int f = (int)(idx % F);
+    const int64_t row = ro.off[f] + (int64_t)ids[idx];
+    const uint32_t bit = 1u << (row & 31);
+    uint32_t old = 0;
+    if (lane == 0) old = atomicOr(&pre[row >> 5], bit);
+    old = __shfl_sync(0xffffffffu, old, 0);
+    if (old & bit) continue;                                   // another lookup of the same row owns it
+    const bool hit = (touched[row >> 5] >> (row & 31)) & 1u;
+    const int64_t base = row * (int64_t)E;
+    for (int c = lane; c < E; c += 32) {
+      const float gg = hit ? g[base + c] : 0.f;
+      float pp = p[base + c], mm = m[base + c], vv = v[base + c];
+      adamw_one(pp, mm, vv, gg, a);
+      p[base + c] = pp;
+      m[base + c] = mm;
+      v[base + c] = vv;
+      if (hit) g[base + c] = 0.f;
+    }
+  }
+}
+
+// ever |= touched ; touched = 0   (after the sweep; replaces the memset of the touched bitmap)
+__global__ void __launch_bounds__(256) fold_touched_kernel(uint32_t* __restrict__ ever, uint32_t* __restrict__ touched, int64_t nwords) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t t = touched[i];
+    if (t != 0u) {
+      ever[i] |= t;
+      touched[i] = 0u;
+    }
+  }
+}
+
 // hyper = [lr, b1, b2, eps, wd, alpha, step]: advances the step counter and refreshes the folded bias
 // correction ON THE DEVICE, so a CUDA-graph replay of the training step needs no per-step host parameters.
 __global__ void adam_hyper_advance_kernel(float* hyper) {
@@ -150,9 +208,47 @@ __global__ void adam_hyper_advance_kernel(float* hyper) {
 
 using namespace krs;
 
+extern "C" int krs_adamw_cold(float* p, float* m, float* v, float* g, uint32_t* touched, uint32_t* ever, int64_t n, int row_len,
+                              float lr, float b1, float b2, float eps, float wd, int64_t step, const float* hyper_dev,
+                              void* stream);
 extern "C" int krs_adamw(float* p, float* m, float* v, float* g, uint32_t* touched, int64_t n, int row_len, float lr,
                          float b1, float b2, float eps, float wd, int64_t step, const float* hyper_dev, void* stream) {
+  return krs_adamw_cold(p, m, v, g, touched, nullptr, n, row_len, lr, b1, b2, eps, wd, step, hyper_dev, stream);
+}
+
+extern "C" int krs_adamw_skip(float* p, float* m, float* v, float* g, uint32_t* touched, uint32_t* ever, uint32_t* skip,
+                              int64_t n, int row_len, float lr, float b1, float b2, float eps, float wd, int64_t step,
+                              const float* hyper_dev, void* stream);
+extern "C" int krs_adamw_cold(float* p, float* m, float* v, float* g, uint32_t* touched, uint32_t* ever, int64_t n, int row_len,
+                              float lr, float b1, float b2, float eps, float wd, int64_t step, const float* hyper_dev,
+                              void* stream) {
+  return krs_adamw_skip(p, m, v, g, touched, ever, nullptr, n, row_len, lr, b1, b2, eps, wd, step, hyper_dev, stream);
+}
+
+extern "C" int krs_adamw_rows(float* p, float* m, float* v, float* g, const uint32_t* touched, uint32_t* pre,
+                              const int32_t* ids, const int64_t* row_off, int64_t B, int F, int E, float lr, float b1, float b2,
+                              float eps, float wd, int64_t step, void* stream) {
+  KRS_REQUIRE(p && m && v && g && touched && pre && ids && row_off, "krs_adamw_rows: null argument");
+  KRS_REQUIRE(F >= 1 && F <= 64 && E >= 1 && B >= 0 && step >= 1, "krs_adamw_rows: bad F/E/B/step");
+  if (B == 0) return KRS_OK;
+  RowOffsets ro;
+  for (int f = 0; f < F; ++f) ro.off[f] = row_off[f];
+  AdamArgs a;
+  a.lr = lr; a.b1 = b1; a.b2 = b2; a.eps = eps; a.wd = wd;
+  a.alpha = (float)((double)lr * sqrt(1.0 - pow((double)b2, (double)step)) / (1.0 - pow((double)b1, (double)step)));
+  const int64_t n_lookups = B * (int64_t)F;
+  const unsigned grid = (unsigned)krs::imax<int64_t>(1, krs::imin<int64_t>(ceil_div<int64_t>(n_lookups, 8), (int64_t)sm_count() * 32));
+  adamw_rows_kernel<<<grid, 256, 0, as_stream(stream)>>>(p, m, v, g, touched, pre, ids, ro, n_lookups, F, E, a);
+  KRS_LAUNCH_CHECK();
+  return KRS_OK;
+}
+
+extern "C" int krs_adamw_skip(float* p, float* m, float* v, float* g, uint32_t* touched, uint32_t* ever, uint32_t* skip,
+                              int64_t n, int row_len, float lr, float b1, float b2, float eps, float wd, int64_t step,
+                              const float* hyper_dev, void* stream) {
   KRS_REQUIRE(p && m && v && g, "krs_adamw: null argument");
+  KRS_REQUIRE(skip == nullptr || touched != nullptr, "krs_adamw_skip: the skip bitmap needs the gradient arena");
+  KRS_REQUIRE(ever == nullptr || touched != nullptr, "krs_adamw_cold: the ever-touched bitmap needs the gradient arena");
   KRS_REQUIRE(n >= 0 && (step >= 1 || hyper_dev != nullptr), "krs_adamw: bad n/step");
   KRS_REQUIRE(touched == nullptr || (row_len > 0 && n % row_len == 0), "krs_adamw: arena needs n %% row_len == 0");
   if (n == 0) return KRS_OK;
@@ -163,11 +259,12 @@ extern "C" int krs_adamw(float* p, float* m, float* v, float* g, uint32_t* touch
                       : (float)((double)lr * sqrt(1.0 - pow((double)b2, (double)step)) / (1.0 - pow((double)b1, (double)step)));
   const bool vec = (n % 4 == 0) && aligned16(p) && aligned16(m) && aligned16(v) && aligned16(g) &&
                    (touched == nullptr || row_len % 4 == 0);
+  KRS_REQUIRE(skip == nullptr || vec, "krs_adamw_skip: the skip bitmap needs the vector path (n %% 4 == 0, row_len %% 4 == 0, 16-byte aligned)");
   const int64_t work = vec ? n / 4 : n;
   const unsigned grid = (unsigned)krs::imax<int64_t>(1, krs::imin<int64_t>(ceil_div<int64_t>(work, 256), (int64_t)sm_count() * 32));
   if (vec) {
-    if (touched) adamw_vec_kernel<true><<<grid, 256, 0, s>>>(p, m, v, g, touched, work, row_len / 4, a, hyper_dev);
-    else adamw_vec_kernel<false><<<grid, 256, 0, s>>>(p, m, v, g, nullptr, work, 1, a, hyper_dev);
+    if (touched) adamw_vec_kernel<true><<<grid, 256, 0, s>>>(p, m, v, g, touched, ever, skip, work, row_len / 4, a, hyper_dev);
+    else adamw_vec_kernel<false><<<grid, 256, 0, s>>>(p, m, v, g, nullptr, nullptr, nullptr, work, 1, a, hyper_dev);
   } else {
     if (touched) adamw_scalar_kernel<true><<<grid, 256, 0, s>>>(p, m, v, g, touched, n, row_len, a, hyper_dev);
     else adamw_scalar_kernel<false><<<grid, 256, 0, s>>>(p, m, v, g, nullptr, n, 1, a, hyper_dev);
@@ -175,7 +272,15 @@ extern "C" int krs_adamw(float* p, float* m, float* v, float* g, uint32_t* touch
   KRS_LAUNCH_CHECK();
   if (touched) {
     const int64_t rows = n / row_len;
-    KRS_CUDA(cudaMemsetAsync(touched, 0, sizeof(uint32_t) * (size_t)ceil_div<int64_t>(rows, 32), s));
+    const int64_t nwords = ceil_div<int64_t>(rows, 32);
+    if (ever != nullptr) {     // (the scalar kernel ignores `ever` and does the full update; the fold keeps it valid)
+      fold_touched_kernel<<<(unsigned)krs::imax<int64_t>(1, krs::imin<int64_t>(ceil_div<int64_t>(nwords, 256), (int64_t)sm_count() * 8)), 256, 0, s>>>(
+          ever, touched, nwords);
+      KRS_LAUNCH_CHECK();
+    } else {
+      KRS_CUDA(cudaMemsetAsync(touched, 0, sizeof(uint32_t) * (size_t)nwords, s));
+    }
+    if (skip != nullptr) KRS_CUDA(cudaMemsetAsync(skip, 0, sizeof(uint32_t) * (size_t)nwords, s));
   }
   return KRS_OK;
 }

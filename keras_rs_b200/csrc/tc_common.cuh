@@ -161,6 +161,14 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
 __device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile_addr, int kstep) {
   return make_desc(tile_addr + kstep * 32, 16, 512, 4);
 }
+// lo half of the 3xTF32 split of x given hi = trunc_tf32(x): the residual x - hi is exact in fp32; rounding it to TF32
+// (nearest, ties away) = adding half an ulp of the 13 dropped mantissa bits to its bit pattern — the tensor core ignores
+// those 13 bits, so no final mask is needed.  cvt.rna.tf32.f32 compiles to ~4 instructions (inf/nan guard, add, mask) on
+// sm_100a; this is one integer add after the subtraction (differs from cvt.rna only for inf / nan inputs).
+__device__ __forceinline__ float tf32_lo_of(float x) {
+  const float h = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  return __uint_as_float(__float_as_uint(x - h) + 0x1000u);
+}
 __device__ __forceinline__ float tf32_rna_f(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));

@@ -92,6 +92,9 @@ class DCN(torch.nn.Module):
         self.emb_touched = torch.zeros((self.total_rows // 32,), dtype=torch.int32, device=self.device_)
         self.emb._krs_arena = self.emb_grad
         self.emb._krs_touched = self.emb_touched
+        # rows that have ever received a gradient (AdamW sweeps the others with a decay-only update, krs_adamw_cold)
+        self.emb_ever = torch.zeros_like(self.emb_touched)
+        self.emb._krs_ever = self.emb_ever
 
     # ------------------------------------------------------------------ parameters
     def tables(self):
@@ -298,6 +301,70 @@ class DCN(torch.nn.Module):
         b[key].replay()
         optimizer.iterations += 1
         return b["loss"]
+
+    # ------------------------------------------------------------------ pipelined AdamW (single GPU)
+    def train_on_batch_pipelined(self, ids, labels, optimizer: optimizers.AdamW, next_ids, denom: int = 0):
+        """Same result as train_on_batch (bit for bit) with the table sweep taken off the critical path: only the rows the
+        NEXT batch gathers (`next_ids`, (B, F)) get this step's AdamW update on the main stream (krs_adamw_rows); every
+        other row is swept on a side stream under the next step's forward / backward (krs_adamw_skip).  The scatter of step
+        t+1 writes arena rows and a touched bitmap the cold sweep of step t never reads (double-buffered bitmaps; the rows
+        it scatters to are exactly the pre-updated ones the sweep skips).  Call finish_pipeline() before reading the
+        tables or switching back to train_on_batch."""
+        if not isinstance(optimizer, optimizers.AdamW) or getattr(optimizer, "_hyper_dev", None) is not None:
+            raise ValueError("train_on_batch_pipelined needs a host-stepped AdamW / Adam optimizer")
+        B = ids.shape[0]
+        b = self._step_buffers(B)
+        st = getattr(self, "_pipe", None)
+        if st is None:
+            st = self._pipe = dict(side=torch.cuda.Stream(device=self.device_), cold_done=None, cur=0,
+                                   touched=[self.emb_touched, torch.zeros_like(self.emb_touched)],
+                                   pre=torch.zeros_like(self.emb_touched),
+                                   row_off=(C.c_int64 * self.F)(*[int(o) for o in self.row_off]))
+        if "next_ids" not in b:
+            b["next_ids"] = torch.empty_like(b["ids"])
+        cur = st["cur"]
+        t_cur = st["touched"][cur]
+        for f in range(self.F):                              # this step's scatter marks rows in the current bitmap
+            b["plan"].arr[f].touched = t_cur[self.row_off[f] // 32:].data_ptr()
+        loss = self.forward_backward(ids, labels, denom)
+        self._sync_gradients()
+        optimizer.iterations += 1
+        main = torch.cuda.current_stream(self.device_)
+        if st["cold_done"] is not None:
+            main.wait_event(st["cold_done"])                 # step t-1's sweep has reached every row
+        slots = optimizer._slots(self.emb, ("m", "v"))
+        hyp = (optimizer.learning_rate, optimizer.beta_1, optimizer.beta_2, optimizer.epsilon, optimizer.weight_decay,
+               max(optimizer.iterations, 1))
+        with torch.no_grad():
+            optimizer._update(self.dense_flat, self.dense_grad_flat, None)
+            b["next_ids"].copy_(next_ids if next_ids.dtype == torch.int32 else next_ids.to(torch.int32), non_blocking=True)
+            check(lib.krs_adamw_rows(ptr(self.emb), ptr(slots["m"]), ptr(slots["v"]), ptr(self.emb_grad), ptr(t_cur), ptr(st["pre"]),
+                                     ptr(b["next_ids"]), st["row_off"], B, self.F, self.E, *hyp, stream()))
+            hot_done = torch.cuda.Event()
+            hot_done.record(main)
+            side = st["side"]
+            side.wait_event(hot_done)
+            with torch.cuda.stream(side):
+                check(lib.krs_adamw_skip(ptr(self.emb), ptr(slots["m"]), ptr(slots["v"]), ptr(self.emb_grad), ptr(t_cur),
+                                         ptr(getattr(self, "emb_ever", None)), ptr(st["pre"]), self.emb.numel(), self.E, *hyp, None,
+                                         side.cuda_stream))
+                st["cold_done"] = torch.cuda.Event()
+                st["cold_done"].record(side)
+        st["cur"] = cur ^ 1
+        self._end_of_step()
+        return loss
+
+    def finish_pipeline(self):
+        """Joins the side stream of train_on_batch_pipelined and restores the single touched bitmap of train_on_batch."""
+        st = getattr(self, "_pipe", None)
+        if st is None:
+            return
+        if st["cold_done"] is not None:
+            torch.cuda.current_stream(self.device_).wait_event(st["cold_done"])
+        for b in self._bufs.values():
+            for f in range(self.F):
+                b["plan"].arr[f].touched = self.emb_touched[self.row_off[f] // 32:].data_ptr()
+        st["cur"] = 0
 
     def _end_of_step(self):
         """Hook for cross-rank ordering at the end of a step (row-sharded model)."""

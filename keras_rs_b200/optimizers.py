@@ -72,6 +72,16 @@ class AdamW(Optimizer):
     def _update(self, p, g, touched):
         st = self._slots(p, ("m", "v"))
         row_len = p.shape[-1] if (touched is not None and p.dim() >= 2) else 1
+        ever = getattr(p, "_krs_ever", None) if touched is not None else None
+        if ever is not None and not getattr(p, "_krs_ever_owner", None) in (None, id(self)):
+            ever = None                     # the bitmap describes the moments of ONE optimizer instance
+        if ever is not None:
+            # rows that never received a gradient hold m = v = 0: decay-only update, 8 instead of 24 bytes per parameter
+            p._krs_ever_owner = id(self)
+            check(lib.krs_adamw_cold(ptr(p), ptr(st["m"]), ptr(st["v"]), ptr(g), ptr(touched), ptr(ever), p.numel(), row_len,
+                                     self.learning_rate, self.beta_1, self.beta_2, self.epsilon, self.weight_decay,
+                                     max(self.iterations, 1), ptr(getattr(self, "_hyper_dev", None)), stream()))
+            return
         check(lib.krs_adamw(ptr(p), ptr(st["m"]), ptr(st["v"]), ptr(g), ptr(touched), p.numel(), row_len,
                             self.learning_rate, self.beta_1, self.beta_2, self.epsilon, self.weight_decay,
                             max(self.iterations, 1), ptr(getattr(self, "_hyper_dev", None)), stream()))

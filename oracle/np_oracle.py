@@ -501,6 +501,84 @@ def dcn_backward(params: dict, ids: np.ndarray, dpred: np.ndarray, cache: dict) 
     return dict(tables=tg, cross=cross_g, mlp=mlp_g)
 
 
+# --------------------------------------------------------------------------- DLRM (examples/ml_perf/model.py:175-212)
+def dlrm_forward(params: dict, dense_in: np.ndarray, ids: np.ndarray, interaction: str = "dot", cache: dict | None = None):
+    """params: tables [(V,E)], bottom [(W,b)], top [(W,b)], cross [dict(V,b,U)] ; bottom layers relu, top relu ... sigmoid.
+    interaction "dot": DotInteraction over [bottom, e_1..e_F] behind the bottom output (classic DLRM, BASELINE C3);
+    "cross": DCNBlock over concat([bottom, e_1..e_F]) (model.py:204-208,332-336)."""
+    c = {} if cache is None else cache
+    h = dense_in
+    c["bottom_in"], c["bottom_out"] = [], []
+    for W, b in params["bottom"]:
+        c["bottom_in"].append(h)
+        h = dense(h, W, b, "relu")
+        c["bottom_out"].append(h)
+    embs = [embedding_lookup(t, ids[:, f]) for f, t in enumerate(params["tables"])]
+    c["embs"], c["bottom"] = embs, h
+    if interaction == "dot":
+        feats = [h] + embs
+        z = dot_interaction(feats)
+        x = np.concatenate([h, z], axis=-1)
+    else:
+        x0 = np.concatenate([h] + embs, axis=-1)
+        x = x0
+        c["x0"], c["cross_in"] = x0, []
+        for layer in params["cross"]:
+            c["cross_in"].append(x)
+            x = feature_cross(x0, x, layer["V"], layer.get("b"), layer.get("U"))
+    c["top_in"], c["top_out"] = [], []
+    n = len(params["top"])
+    for i, (W, b) in enumerate(params["top"]):
+        c["top_in"].append(x)
+        x = dense(x, W, b, "sigmoid" if i == n - 1 else "relu")
+        c["top_out"].append(x)
+    return x
+
+
+def dlrm_backward(params: dict, ids: np.ndarray, dpred: np.ndarray, cache: dict, interaction: str = "dot") -> dict:
+    """Analytic gradients of dlrm_forward w.r.t. every parameter (dense (V,E) table gradients)."""
+    g = dpred
+    n = len(params["top"])
+    gtop = [None] * n
+    for i in range(n - 1, -1, -1):
+        W, b = params["top"][i]
+        r = dense_bwd(g, cache["top_in"][i], W, b, "sigmoid" if i == n - 1 else "relu", cache["top_out"][i])
+        gtop[i] = (r["dW"], r["db"])
+        g = r["dx"]
+    E = cache["bottom"].shape[1]
+    F = len(params["tables"])
+    out = dict(top=gtop, cross=[])
+    if interaction == "dot":
+        gh = g[:, :E].copy()
+        dfeats = dot_interaction_bwd(g[:, E:], [cache["bottom"]] + cache["embs"])
+        gh = gh + dfeats[0]
+        gembs = dfeats[1:]
+    else:
+        gx0 = np.zeros_like(cache["x0"])
+        gcross = [None] * len(params["cross"])
+        for i in range(len(params["cross"]) - 1, -1, -1):
+            layer = params["cross"][i]
+            r = feature_cross_bwd(g, cache["x0"], cache["cross_in"][i], layer["V"], layer.get("b"), layer.get("U"))
+            gcross[i] = {k: r[k] for k in ("dV", "db", "dU") if k in r and r[k] is not None}
+            gx0 = gx0 + r["dx0"]
+            g = r["dx"]
+        gx0 = gx0 + g                      # the first layer's x is x0
+        out["cross"] = gcross
+        gh = gx0[:, :E]
+        gembs = [gx0[:, E * (f + 1):E * (f + 2)] for f in range(F)]
+    out["tables"] = [embedding_grad(ids[:, f], None, params["tables"][f].shape[0], gembs[f], reduce=False) for f in range(F)]
+    nb = len(params["bottom"])
+    gbot = [None] * nb
+    g = gh
+    for i in range(nb - 1, -1, -1):
+        W, b = params["bottom"][i]
+        r = dense_bwd(g, cache["bottom_in"][i], W, b, "relu", cache["bottom_out"][i])
+        gbot[i] = (r["dW"], r["db"])
+        g = r["dx"]
+    out["bottom"] = gbot
+    return out
+
+
 def glorot_uniform(rng: np.random.Generator, fan_in: int, fan_out: int) -> np.ndarray:
     limit = math.sqrt(6.0 / (fan_in + fan_out))
     return rng.uniform(-limit, limit, size=(fan_in, fan_out)).astype(F32)

@@ -1,4 +1,5 @@
 """Debug harness: per-role clock64 timeline of CTA 0 of one tcgen05 GEMM (cross forward, C2 shape).
+Needs a trace build of the library: touch keras_rs_b200/csrc/gemm_tc.cu && KRS_EXTRA_FLAGS=-DKRS_TC_TRACE=1 bash keras_rs_b200/csrc/build.sh
 ENGINE=tcgen05|tcgen05_ts  MODE=cross|cross_noh2|cross_x1|dense|sgemm"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -46,7 +47,7 @@ print("entries", len(ev))
 by = {k: [(i, c - t0) for tag, i, c in ev if tag == k] for k in names}
 for k in (6, 7):
     print(names[k], by[k][:6])
-KB = 52   # k-blocks per tile at K = 832
+KB = 26 if ENGINE == "tcgen05_ts" else 52   # ring stages per tile at K = 832 (tcgen05_ts moves 32 k per stage)
 def per_tile(tag, tile):
     """{kb: clock} of this tag's events inside the tile-th visit (events are in time order; kb restarts at 0 per tile)."""
     out, seen_tile, prev = {}, -1, 10 ** 9

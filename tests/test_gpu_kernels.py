@@ -457,6 +457,29 @@ def test_topk_tc_candidate_ids_and_large_slice(K):
         K.ops.set_topk_engine("auto")
 
 
+@pytest.mark.parametrize("nq,nc,d,k", [(260, 100_003, 64, 50), (33, 5000, 32, 100), (129, 3000, 48, 1)])
+def test_topk_tc_with_precomputed_lo_plane(K, nq, nc, d, k):
+    """tensor-pipe path with the candidates' lo plane streamed by TMA (krs_topk_lo): same results as the in-kernel split."""
+    K.ops.set_topk_engine("tcgen05")
+    try:
+        rng = np.random.default_rng(nq + nc)
+        q = rng.normal(size=(nq, d)).astype(np.float32)
+        c = rng.normal(size=(nc, d)).astype(np.float32)
+        tc_, tq = dev(c), dev(q)
+        lo = K.ops.split_candidates_lo(tc_)
+        x = npy(tc_)
+        hi = (x.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+        assert np.abs(npy(lo) - (x - hi)).max() <= np.abs(x - hi).max() * 2.0 ** -10      # lo = tf32_rn(x - trunc_tf32(x))
+        s0, i0 = K.ops.top_k_scores(tq, tc_, None, k)
+        s1, i1 = K.ops.top_k_scores(tq, tc_, None, k, cand_lo=lo)
+        np.testing.assert_array_equal(npy(s0), npy(s1))          # identical arithmetic, only the producer of C_lo differs
+        np.testing.assert_array_equal(npy(i0), npy(i1))
+        ref = q.astype(np.float64) @ c.astype(np.float64).T
+        _check_topk(ref, npy(s1), npy(i1), k)
+    finally:
+        K.ops.set_topk_engine("auto")
+
+
 def test_retrieval_shared_variable_pattern(K):
     # examples/basic_retrieval.py:249-257: assign another layer's embedding variable, then call
     emb = K.layers.Embedding(50, 16)
@@ -510,6 +533,43 @@ def test_adamw_dense_and_arena_match_oracle(K):
         assert_close(npy(pd_), p, rel=2e-6, what="adamw dense")
         np.testing.assert_array_equal(npy(pa), npy(pd_))            # arena path == dense path, bitwise
         assert float(arena.abs().max()) == 0.0 and int(touched.abs().max()) == 0   # arena re-zeroed
+
+
+def test_adamw_cold_rows_are_bitwise_equal_to_the_dense_update(K):
+    """krs_adamw_cold: rows that never received a gradient get the decay-only update; parameters AND moments must stay
+    bit-identical to the dense rule over several steps, and the ever-touched bitmap must accumulate the touched rows."""
+    rng = np.random.default_rng(53)
+    V, E = 4096, 32
+    p0 = rng.normal(size=(V, E)).astype(np.float32)
+    opt_d, opt_c = K.optimizers.AdamW(learning_rate=0.01), K.optimizers.AdamW(learning_rate=0.01)
+    pd_, pc = dev(p0.copy()), dev(p0.copy())
+    arena = torch.zeros_like(pc)
+    touched = torch.zeros((V // 32,), dtype=torch.int32, device="cuda")
+    ever = torch.zeros_like(touched)
+    pc._krs_arena, pc._krs_touched, pc._krs_ever = arena, touched, ever
+    seen = np.zeros((V,), bool)
+    for step in range(6):
+        rows = rng.choice(V, size=200, replace=False)
+        g = np.zeros_like(p0)
+        g[rows] = rng.normal(size=(200, E)).astype(np.float32)
+        pd_.grad = dev(g)
+        opt_d.apply([pd_])
+        arena.copy_(dev(g))
+        bits = np.zeros((V // 32,), np.uint32)
+        for r in rows:
+            bits[r >> 5] |= np.uint32(1 << (r & 31))
+        touched.copy_(dev(bits.view(np.int32)))
+        opt_c.apply([pc])
+        seen[rows] = True
+        np.testing.assert_array_equal(npy(pc), npy(pd_))
+        for slot in ("m", "v"):
+            np.testing.assert_array_equal(npy(opt_c._state[id(pc)][slot]), npy(opt_d._state[id(pd_)][slot]))
+        got = npy(ever).view(np.uint32)
+        exp = np.zeros((V // 32,), np.uint32)
+        for r in np.nonzero(seen)[0]:
+            exp[r >> 5] |= np.uint32(1 << (r & 31))
+        np.testing.assert_array_equal(got, exp)
+        assert float(arena.abs().max()) == 0.0 and int(touched.abs().max()) == 0
 
 
 @pytest.mark.parametrize("name", ["sgd", "adagrad"])
