@@ -48,9 +48,6 @@ def parse():
     ap.add_argument("--graph", action="store_true", help="replay the step from a CUDA graph (1 GPU; the eager step already has no launch gaps)")
     ap.add_argument("--projection-dim", type=int, default=0, help="low-rank FeatureCross (ml_perf uses 512); 0 = full rank")
     ap.add_argument("--dense-units", default="192,192")
-    ap.add_argument("--pipeline-adamw", action="store_true",
-                    help="1 GPU, AdamW: update the next batch's rows first and sweep the rest of the tables on a side stream "
-                         "under the next step (DCN.train_on_batch_pipelined; same results bit for bit)")
     return ap.parse_args()
 
 
@@ -184,18 +181,14 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup, finalize=None):
+    def timed(fn, steps, warmup):
         for i in range(warmup):
             fn(i)
-        if finalize:
-            finalize()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(steps):
             fn(warmup + i)
-        if finalize:
-            finalize()              # joins side-stream work so that it is inside the timed region
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -217,20 +210,14 @@ def run_ours(a):
             use_graph = False
     train = model.train_on_batch_graph if use_graph else model.train_on_batch
 
-    pipelined = a.pipeline_adamw and world == 1 and a.optimizer == "adamw" and not use_graph
-    finalize = model.finish_pipeline if pipelined else None
-
     def step_dev(i):
-        if pipelined:
-            model.train_on_batch_pipelined(dev_ids[i % NB], dev_y[i % NB], opt, dev_ids[(i + 1) % NB], denom)
-        else:
-            train(dev_ids[i % NB], dev_y[i % NB], opt, denom)
+        train(dev_ids[i % NB], dev_y[i % NB], opt, denom)
 
     clocks = Clocks(local)
     if rank == 0:
         clocks.start()
     split0 = lib.krs_gemm_split_launch_count()
-    ms_total = timed(step_dev, a.steps, a.warmup, finalize)
+    ms_total = timed(step_dev, a.steps, a.warmup)
     split_launches = (lib.krs_gemm_split_launch_count() - split0) * a.steps // (a.steps + a.warmup)   # timed steps only
     clk = clocks.stop() if rank == 0 else None
     ms_step = ms_total / a.steps
@@ -240,13 +227,10 @@ def run_ours(a):
     loss_host = torch.zeros((a.steps + a.warmup + 1,), dtype=torch.float32).pin_memory()
 
     def step_e2e(i):
-        if pipelined:
-            loss = model.train_on_batch_pipelined(host_ids[i % NB], host_y[i % NB], opt, host_ids[(i + 1) % NB], denom)
-        else:
-            loss = train(host_ids[i % NB], host_y[i % NB], opt, denom)
+        loss = train(host_ids[i % NB], host_y[i % NB], opt, denom)
         loss_host[i % loss_host.numel():i % loss_host.numel() + 1].copy_(loss, non_blocking=True)
 
-    ms_e2e = timed(step_e2e, a.steps, 3, finalize) / a.steps
+    ms_e2e = timed(step_e2e, a.steps, 3) / a.steps
     e2e_value = B * world / (ms_e2e * 1e-3)
     h2d = host_ids[0].numel() * 4 + host_y[0].numel() * 4
     final_loss = float(loss_host[(a.steps + 2) % loss_host.numel()])
@@ -403,8 +387,7 @@ def run_ours(a):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a), "global_batch": B * world, "parallelism": f"dp{world}" + (
             "+mod-row-sharded tables over NVLink peer memory" if world > 1 else ""), "gemm_engine": engine,
-            "l2": "inputs_larger_than_L2", "final_loss": final_loss, "launch": "cuda_graph" if use_graph else "eager",
-            "adamw_sweep": "pipelined (next batch's rows first, rest under the next step)" if pipelined else "in step"},
+            "l2": "inputs_larger_than_L2", "final_loss": final_loss, "launch": "cuda_graph" if use_graph else "eager"},
         "clocks": clk,
         "e2e": {"value": e2e_value, "unit": "examples/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4},

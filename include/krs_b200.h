@@ -77,7 +77,9 @@ typedef struct krs_feature {
   float* grad;            /* bwd only: dense (vocab, dim) gradient arena, accumulated into       */
   uint32_t* touched;      /* bwd only: NULL or bitmap of ceil(vocab/32) words, bit r set when    */
                           /*           row r received gradient                                    */
-  int64_t vocab;          /* rows in table (ids are clamped into [0, vocab-1])                   */
+  int64_t vocab;          /* rows in table.  ids < 0 count from the end; ids still outside        */
+                          /* [0, vocab) address no row: NaN row forward, no gradient backward    */
+                          /* (jnp.take mode="fill", the JAX backend of keras.ops.take)           */
   int64_t ids_stride;     /* elements between consecutive samples                                */
   int32_t hotness;        /* H: ids per sample (1 for rank-1 ids)                                */
   int32_t dim;            /* E                                                                   */
@@ -94,17 +96,10 @@ typedef struct krs_feature {
   float* const* shard_grads;
   uint32_t* const* shard_touched; /* bwd only, nullable: per-shard bitmaps indexed by LOCAL row     */
   int32_t num_shards;
-  int32_t shard_mode;     /* low byte: how a sharded feature is addressed; second byte: this rank's shard id  */
-                          /*  0 KRS_SHARD_DIRECT  : row = shard_tables[id%S] + (id/S)*E  (peer-mapped tables)  */
-                          /*  1 KRS_SHARD_OWNER   : only ids with id%S == me; row = table + (id/S)*E (fwd) or */
-                          /*                        grad + (id/S)*E (bwd); other positions are skipped        */
-                          /*  2 KRS_SHARD_POSITION: row = shard_tables[id%S] + pos*E (fwd pull) or            */
-                          /*                        shard_grads[id%S] + pos*E (bwd push, plain stores),       */
-                          /*                        pos = b*F + f: monotonic remote addresses                 */
+  int32_t shard_mode;     /* 0 KRS_SHARD_DIRECT: row = shard_tables[id%S] + (id/S)*E (peer-mapped tables read  */
+                          /* in place; random remote rows are slow — the training path is krs_xchg_* below)   */
 } krs_feature_t;
 #define KRS_SHARD_DIRECT 0
-#define KRS_SHARD_OWNER 1
-#define KRS_SHARD_POSITION 2
 
 /* features: HOST array of F descriptors (copied into kernel parameters; F <= 96 per call).
  * out: (B, out_ld) fp32. */
@@ -179,12 +174,6 @@ int krs_dot_bwd(const float* const* feats, const int64_t* strides, const float* 
  * Q (nq,d), C (nc,d), cand_ids nullable int32 (nc).  top_scores (nq,k) fp32, top_ids (nq,k) int32.
  * workspace: krs_topk_workspace_bytes(). */
 size_t krs_topk_workspace_bytes(int64_t nq, int64_t nc, int d, int k);
-/* Same, with the candidates' low-order TF32 plane C_lo (nullable) precomputed by krs_topk_split_candidates: the tensor-pipe
- * kernel then streams both planes by TMA and no thread touches a candidate element before the tensor core does. */
-int krs_topk_lo(const float* Q, const float* C, const float* C_lo, const int32_t* cand_ids, float* top_scores,
-                int32_t* top_ids, int64_t nq, int64_t nc, int d, int k, void* workspace, size_t workspace_bytes,
-                void* stream);
-int krs_topk_split_candidates(const float* C, float* C_lo, int64_t nc, int d, void* stream);
 /* Score engine of krs_topk: 0 = auto (tensor pipe when the problem fills the machine and the shape is eligible:
  * d % 4 == 0, d <= 64, k <= 128, nc >= 96), 1 = exact-fp32 FMA score tiles only, 2 = tcgen05 (3xTF32, fp32-level
  * accuracy) whenever eligible.  krs_topk_tc_launch_count() lets tests prove which kernel produced a result. */
@@ -218,16 +207,6 @@ int krs_adamw(float* p, float* m, float* v, float* g, uint32_t* touched, int64_t
  * decay of p alone and the sweep moves 8 instead of 24 bytes per parameter; `ever |= touched` is folded in after the sweep. */
 int krs_adamw_cold(float* p, float* m, float* v, float* g, uint32_t* touched, uint32_t* ever, int64_t n, int row_len,
                    float lr, float b1, float b2, float eps, float wd, int64_t step, const float* hyper_dev, void* stream);
-/* Pipelined step: krs_adamw_rows applies the step's update to the rows the NEXT batch will gather (ids (B,F) int32 with per-feature
- * row offsets into the arena-wide table; one update per distinct row, its bit set in `pre`), so that the next gather can start;
- * krs_adamw_skip then sweeps every row whose `skip` (= pre) bit is clear — on any stream, e.g. under the next step's forward and
- * backward — folds / clears `touched` and clears `skip`.  Together they equal one krs_adamw call, bit for bit. */
-int krs_adamw_rows(float* p, float* m, float* v, float* g, const uint32_t* touched, uint32_t* pre, const int32_t* ids,
-                   const int64_t* row_off, int64_t B, int F, int E, float lr, float b1, float b2, float eps, float wd,
-                   int64_t step, void* stream);
-int krs_adamw_skip(float* p, float* m, float* v, float* g, uint32_t* touched, uint32_t* ever, uint32_t* skip, int64_t n,
-                   int row_len, float lr, float b1, float b2, float eps, float wd, int64_t step, const float* hyper_dev,
-                   void* stream);
 /* Advances hyper_dev[6] (step) and refreshes hyper_dev[5] (alpha) on the device, so a captured CUDA graph of
  * the training step can be replayed without per-step host parameters. */
 int krs_adam_hyper_advance(float* hyper_dev, void* stream);
@@ -243,6 +222,66 @@ int krs_sgd_adagrad(float* p, float* acc, float* g, uint32_t* touched, int64_t n
  * tensorflow/distributed_embedding.py:316-328) and per-owner counts (S ints, pre-zeroed). */
 int krs_mod_route(const void* ids, int ids_i64, int64_t n, int S, int32_t* owner, int64_t* local,
                   int32_t* counts, void* stream);
+
+/* ------------------------------------------------------------------ row-sharded exchange over peer memory (C5)
+ * The B200 form of the reference's SparseCore protocol (ids routed to the owner, owner-side lookup, activations
+ * returned, optimizer applied on the owner without a dense gradient: jax/embedding_utils.py:144-217,
+ * jax/embedding_lookup.py:174-273).  Every rank owns one cudaIpc-exported REGION that all peers map; the caller
+ * chooses the layout (byte offsets below, identical on every rank):
+ *   flags  : uint32[KRS_XCHG_MAX_SHARDS + 1]   barrier epochs written by the peers + one error word
+ *   hdr    : int32[2][KRS_XCHG_MAX_SHARDS + 1] bucket starts of the request lists, double buffered by step parity
+ *   rows   : int32[2][B*F]                     request lists: arena row ON THE OWNER, bucket o at hdr[o]
+ *   pos    : int32[2][B*F]                     position b*F+f of that request in the requester's activation
+ *   x0     : float[B*F*E]                      the requester's concatenated activation (owners write into it)
+ *   grad   : float[B*F*E]                      dL/dx0 (owners read from it)
+ * ids < 0 count from the end of the table, ids still outside [0, vocab) have no owner: their activation row is NaN
+ * and they receive no gradient (jnp.take mode="fill", the JAX backend of keras.ops.take). */
+#define KRS_XCHG_MAX_SHARDS 16
+typedef struct krs_xchg {
+  int32_t S, me, F, E;
+  int64_t B;                                  /* samples per rank */
+  void* peer_base[KRS_XCHG_MAX_SHARDS];       /* region of rank s as mapped in THIS process ([me] = local)      */
+  int64_t off_flags, off_hdr, off_rows, off_pos, off_x0, off_grad;
+} krs_xchg_t;
+size_t krs_xchg_route_workspace_bytes(int64_t B, int F, int S);
+/* Requester: stable counting sort of the local ids (B, ids_ld) by owner into rows/pos/hdr[parity] of my region.
+ * vocab_dev: device int64[F] GLOBAL vocabulary sizes; owner_row_off_dev: device int32[S*F], first arena row of
+ * table f on owner o.  fill_invalid_nan: write NaN rows into my x0 for ids without an owner. */
+int krs_xchg_route(const krs_xchg_t* x, int parity, const void* ids, int ids_i64, int64_t ids_ld,
+                   const int64_t* vocab_dev, const int32_t* owner_row_off_dev, int32_t* workspace,
+                   int fill_invalid_nan, void* stream);
+/* All ranks: stream-ordered barrier through the flag arrays (epoch must increase by one per barrier, same sequence
+ * on every rank).  A peer that does not arrive within timeout_s sets bit p of the error word instead of hanging. */
+int krs_xchg_barrier(const krs_xchg_t* x, uint32_t epoch, double timeout_s, void* stream);
+/* Owner: ONE launch serving every requester's bucket for this rank: rows of the local shard `arena` (rows, E) are
+ * written into the requesters' x0.  touched (nullable): bit per local arena row, set for every requested row. */
+int krs_xchg_gather_push(const krs_xchg_t* x, int parity, const float* arena, uint32_t* touched, void* stream);
+/* Slot numbering of the touched rows: slot(row) = blockbase[row >> 15] + wordprefix[row >> 5] + popc(bits below).
+ * wordprefix: uint32[nwords]; blockbase: uint32[krs_slot_scan_blocks(rows)]; n_unique: device scalar. */
+size_t krs_slot_scan_blocks(int64_t nrows);
+int krs_slot_scan(const uint32_t* touched, int64_t nwords, uint32_t* wordprefix, uint32_t* blockbase,
+                  uint32_t* n_unique, void* stream);
+/* Owner: ONE launch pulling the gradient rows of every requester's bucket from the peers' `grad` buffers and
+ * accumulating them (duplicates combined) into compact (cap_rows, E), which must be zero on entry; uniq_rows[slot]
+ * receives the arena row.  More distinct rows than cap_rows sets bit 31 of the error word. */
+int krs_xchg_grad_pull(const krs_xchg_t* x, int parity, const uint32_t* touched, const uint32_t* wordprefix,
+                       const uint32_t* blockbase, float* compact, int32_t* uniq_rows, int64_t cap_rows, void* stream);
+/* Row-sparse optimizers fused onto the compact gradient rows (TableConfig.optimizer, base_distributed_embedding.py:
+ * 176-186; the supported set is the reference's, jax/config_conversion.py:211-288; oracle jax/test_utils.py:474-497):
+ * only rows that received gradient are visited — for SGD / Adagrad that IS the dense rule (g = 0 changes nothing);
+ * Adam and FTRL are the per-row ("lazy") forms the SparseCore path applies.  For slot < *n_unique: row = uniq_rows[slot],
+ * g = compact[slot]; p (and the slot variables s1, s2) are updated in place, compact[slot] is re-zeroed.
+ * hyper (host, 8 floats): SGD [lr] | Adagrad [lr, eps] | Adam [lr, b1, b2, eps, alpha] (alpha = lr*sqrt(1-b2^t)/
+ * (1-b1^t)) | FTRL [lr, lr_power, l1, l2, beta] (keras Ftrl with l2_shrinkage = 0). */
+enum { KRS_OPT_SGD = 0, KRS_OPT_ADAGRAD = 1, KRS_OPT_ADAM = 2, KRS_OPT_FTRL = 3 };
+int krs_rows_apply(float* p, float* s1, float* s2, float* compact, const int32_t* uniq_rows, const uint32_t* n_unique,
+                   int64_t cap_rows, int E, int kind, const float* hyper, uint32_t* touched_to_clear /*nullable*/,
+                   int64_t nwords, void* stream);
+/* Dense-semantics AdamW (every row decays, examples/dcn.py:127) reading its gradient from the compact rows:
+ * rows whose touched bit is clear have g = 0; compact rows are re-zeroed and the bitmap is cleared afterwards. */
+int krs_adamw_compact(float* p, float* m, float* v, float* compact, uint32_t* touched, const uint32_t* wordprefix,
+                      const uint32_t* blockbase, int64_t n, int row_len, float lr, float b1, float b2, float eps,
+                      float wd, int64_t step, void* stream);
 
 /* ------------------------------------------------------------------ peer memory (setup only)
  * Row-sharded tables live in cudaMalloc'd arenas exported with cudaIpc so that the fused gather

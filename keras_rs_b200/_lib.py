@@ -76,9 +76,6 @@ _sig("krs_dot_fwd", C.c_int, C.POINTER(C.c_void_p), C.POINTER(i64), i32, i32, i6
 _sig("krs_dot_bwd", C.c_int, C.POINTER(C.c_void_p), C.POINTER(i64), c_f32p, C.POINTER(C.c_void_p),
      C.POINTER(i64), i32, i32, i64, i32, i32, C.c_void_p)
 _sig("krs_topk_workspace_bytes", C.c_size_t, i64, i64, i32, i32)
-_sig("krs_topk_lo", C.c_int, c_f32p, c_f32p, c_f32p, C.c_void_p, c_f32p, C.c_void_p, i64, i64, i32, i32,
-     C.c_void_p, C.c_size_t, C.c_void_p)
-_sig("krs_topk_split_candidates", C.c_int, c_f32p, c_f32p, i64, i32, C.c_void_p)
 _sig("krs_set_topk_engine", C.c_int, i32)
 _sig("krs_topk_tc_launch_count", C.c_longlong)
 _sig("krs_topk", C.c_int, c_f32p, c_f32p, C.c_void_p, c_f32p, C.c_void_p, i64, i64, i32, i32,
@@ -88,15 +85,37 @@ _sig("krs_adamw", C.c_int, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p, i64, i32,
      C.c_float, C.c_float, C.c_float, C.c_float, i64, c_f32p, C.c_void_p)
 _sig("krs_adamw_cold", C.c_int, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p, C.c_void_p, i64, i32, C.c_float,
      C.c_float, C.c_float, C.c_float, C.c_float, i64, c_f32p, C.c_void_p)
-_sig("krs_adamw_rows", C.c_int, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(i64), i64, i32, i32,
-     C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, i64, C.c_void_p)
-_sig("krs_adamw_skip", C.c_int, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p, C.c_void_p, C.c_void_p, i64, i32, C.c_float,
-     C.c_float, C.c_float, C.c_float, C.c_float, i64, c_f32p, C.c_void_p)
 _sig("krs_adam_hyper_advance", C.c_int, c_f32p, C.c_void_p)
 _sig("krs_sgd_adagrad", C.c_int, c_f32p, c_f32p, c_f32p, C.c_void_p, i64, i32, C.c_float, C.c_float,
      i32, C.c_void_p)
 _sig("krs_mod_route", C.c_int, C.c_void_p, i32, i64, i32, C.c_void_p, C.c_void_p, C.c_void_p,
      C.c_void_p)
+XCHG_MAX_SHARDS = 16
+
+
+class KrsXchg(C.Structure):
+    """krs_xchg_t (include/krs_b200.h): one rank's view of the row-sharded exchange regions."""
+    _fields_ = [
+        ("S", C.c_int32), ("me", C.c_int32), ("F", C.c_int32), ("E", C.c_int32), ("B", C.c_int64),
+        ("peer_base", C.c_void_p * XCHG_MAX_SHARDS),
+        ("off_flags", C.c_int64), ("off_hdr", C.c_int64), ("off_rows", C.c_int64), ("off_pos", C.c_int64),
+        ("off_x0", C.c_int64), ("off_grad", C.c_int64),
+    ]
+
+
+_sig("krs_xchg_route_workspace_bytes", C.c_size_t, i64, i32, i32)
+_sig("krs_xchg_route", C.c_int, C.POINTER(KrsXchg), i32, C.c_void_p, i32, i64, C.c_void_p, C.c_void_p, C.c_void_p, i32,
+     C.c_void_p)
+_sig("krs_xchg_barrier", C.c_int, C.POINTER(KrsXchg), C.c_uint32, C.c_double, C.c_void_p)
+_sig("krs_xchg_gather_push", C.c_int, C.POINTER(KrsXchg), i32, c_f32p, C.c_void_p, C.c_void_p)
+_sig("krs_slot_scan_blocks", C.c_size_t, i64)
+_sig("krs_slot_scan", C.c_int, C.c_void_p, i64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p)
+_sig("krs_xchg_grad_pull", C.c_int, C.POINTER(KrsXchg), i32, C.c_void_p, C.c_void_p, C.c_void_p, c_f32p, C.c_void_p, i64,
+     C.c_void_p)
+_sig("krs_rows_apply", C.c_int, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p, C.c_void_p, i64, i32, i32,
+     C.POINTER(C.c_float), C.c_void_p, i64, C.c_void_p)
+_sig("krs_adamw_compact", C.c_int, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p, C.c_void_p, C.c_void_p, i64, i32,
+     C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, i64, C.c_void_p)
 _sig("krs_ipc_alloc", C.c_int, C.POINTER(C.c_void_p), C.c_size_t, C.c_void_p)
 _sig("krs_ipc_open", C.c_int, C.c_void_p, C.POINTER(C.c_void_p))
 _sig("krs_ipc_close", C.c_int, C.c_void_p)
@@ -107,8 +126,10 @@ EXPORTED = [
     "krs_version", "krs_last_error", "krs_device_sm_count", "krs_set_gemm_engine",
     "krs_get_gemm_engine", "krs_gemm_tc_launch_count", "krs_gemm_tc_set_trace", "krs_gemm_set_workspace", "krs_gemm_split_launch_count", "krs_gather_fwd", "krs_gather_bwd", "krs_cross_fwd", "krs_cross_bwd",
     "krs_cross_combine_fwd", "krs_cross_combine_bwd", "krs_dense_fwd", "krs_dense_bwd", "krs_sgemm",
-    "krs_dot_fwd", "krs_dot_bwd", "krs_topk_workspace_bytes", "krs_topk", "krs_topk_lo", "krs_topk_split_candidates", "krs_set_topk_engine", "krs_topk_tc_launch_count", "krs_loss_fwd_bwd",
-    "krs_adamw", "krs_adamw_cold", "krs_adamw_rows", "krs_adamw_skip", "krs_adam_hyper_advance", "krs_sgd_adagrad", "krs_mod_route", "krs_ipc_alloc", "krs_ipc_open",
+    "krs_dot_fwd", "krs_dot_bwd", "krs_topk_workspace_bytes", "krs_topk", "krs_set_topk_engine", "krs_topk_tc_launch_count", "krs_loss_fwd_bwd",
+    "krs_adamw", "krs_adamw_cold", "krs_adam_hyper_advance", "krs_sgd_adagrad", "krs_mod_route",
+    "krs_xchg_route_workspace_bytes", "krs_xchg_route", "krs_xchg_barrier", "krs_xchg_gather_push", "krs_slot_scan_blocks",
+    "krs_slot_scan", "krs_xchg_grad_pull", "krs_rows_apply", "krs_adamw_compact", "krs_ipc_alloc", "krs_ipc_open",
     "krs_ipc_close", "krs_ipc_free", "krs_enable_peer_access",
 ]
 NCCL_EXPORTED = ["krs_nccl_unique_id", "krs_nccl_init", "krs_nccl_destroy", "krs_nccl_all_to_all_v",

@@ -37,8 +37,17 @@ template <typename IdT>
 __device__ __forceinline__ int64_t load_id(const void* ids, int64_t idx) {
   return (int64_t)reinterpret_cast<const IdT*>(ids)[idx];
 }
-__device__ __forceinline__ int64_t clamp_id(int64_t id, int64_t vocab) {
-  return id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+// Index rule of the reference's backend (keras.ops.take on JAX == jnp.take, default mode "fill"; oracle/np_oracle.py
+// embedding_lookup): ids < 0 count from the end of the table; ids still outside [0, vocab) address no row — the forward
+// returns a NaN row for them, the backward drops them.  Returns the row, or -1.
+__device__ __forceinline__ int64_t resolve_id(int64_t id, int64_t vocab) {
+  id += id < 0 ? vocab : 0;
+  return (uint64_t)id < (uint64_t)vocab ? id : -1;
+}
+__device__ __forceinline__ const float* nan_row() { return reinterpret_cast<const float*>(uintptr_t(1)); }   // sentinel "row of NaN"
+__device__ __forceinline__ float4 nan4() {
+  const float q = __int_as_float(0x7fc00000);
+  return make_float4(q, q, q, q);
 }
 __device__ __forceinline__ const float* row_ptr(const krs_feature_t& f, int64_t id) {
   if (f.num_shards > 1) {
@@ -66,7 +75,6 @@ struct FeatLite {
   const float* const* shards;
   int nshards;
   int shard_shift;   // log2(nshards) when it is a power of two, else -1
-  int mode, me;      // KRS_SHARD_* addressing mode and this rank's shard id
 };
 
 template <int LPR, typename IdT, bool SHARDED>
@@ -85,8 +93,6 @@ __global__ void __launch_bounds__(256) gather_fast_kernel(const __grid_constant_
     t.shards = p.f[i].shard_tables;
     t.nshards = p.f[i].num_shards;
     t.shard_shift = (t.nshards > 0 && (t.nshards & (t.nshards - 1)) == 0) ? (31 - __clz(t.nshards)) : -1;
-    t.mode = p.f[i].shard_mode & 0xff;
-    t.me = (p.f[i].shard_mode >> 8) & 0xff;
     sf[i] = t;
   }
   __syncthreads();
@@ -105,14 +111,15 @@ __global__ void __launch_bounds__(256) gather_fast_kernel(const __grid_constant_
     const float* src = nullptr;
     if (r0 + lane < R) {
       const FeatLite& ft = sf[f];
-      const long long id = clamp_id(load_id<IdT>(ft.ids, b * ft.stride), ft.vocab);
-      if (SHARDED) {
+      const long long id = resolve_id(load_id<IdT>(ft.ids, b * ft.stride), ft.vocab);
+      if (id < 0) {
+        src = nan_row();
+      } else if (SHARDED) {
         const int sh = ft.shard_shift;
         const int owner = sh >= 0 ? (int)(id & (ft.nshards - 1)) : (int)(id % ft.nshards);
         const long long local = sh >= 0 ? (id >> sh) : (id / ft.nshards);
-        if (ft.mode == KRS_SHARD_OWNER) src = (owner == ft.me) ? ft.table + local * E : nullptr;   // rows I own, local table
-        else if (ft.mode == KRS_SHARD_POSITION) src = ft.shards[owner] + (r0 + lane) * E;          // monotonic pull from the owner's staging
-        else src = ft.shards[owner] + local * E;      // direct peer-mapped table (random remote rows: slow over NVLink)
+        src = ft.shards[owner] + local * E;      // direct peer-mapped table (random remote rows are slow over NVLink:
+                                                 // the training path routes through exchange.cu instead)
       } else {
         src = ft.table + id * E;
       }
@@ -125,7 +132,8 @@ __global__ void __launch_bounds__(256) gather_fast_kernel(const __grid_constant_
       for (int u = 0; u < U; ++u) {
         const int j = (s0 + u) * RPW + rsub;
         q[u] = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, (unsigned long long)src, j));
-        if (q[u]) v[u] = ldg_nc_f4(q[u] + sub * 4);
+        if (q[u] == nan_row()) v[u] = nan4();
+        else if (q[u]) v[u] = ldg_nc_f4(q[u] + sub * 4);
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -196,20 +204,34 @@ __global__ void __launch_bounds__(256) gather_bulk_kernel(const __grid_constant_
     const int bsel = it & 1;
     const int64_t r0 = t * tile_rows;
     const int nrows = (int)krs::imin<int64_t>(tile_rows, R - r0);
-    // the bulk store that last read this buffer (2 tiles ago) must have finished reading smem
-    if (threadIdx.x == 0) {
-      asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-      mbar_expect_tx(&bars[bsel], (uint32_t)nrows * row_bytes);
+    // rows whose id addresses no table row are not copied: they are written as NaN by their thread and leave the
+    // transaction count (first pass: count them)
+    int bad = 0;
+    for (int i = threadIdx.x; i < nrows; i += blockDim.x) {
+      const int64_t r = r0 + i;
+      const int64_t b = r / F;
+      const int f = (int)(r - b * F);
+      const krs_feature_t& ft = p.f[f];
+      bad += resolve_id(load_id<IdT>(ft.ids, b * ft.ids_stride), ft.vocab) < 0;
     }
+    // the bulk store that last read this buffer (2 tiles ago) must have finished reading smem
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    const int nbad = __syncthreads_count(bad);
+    if (threadIdx.x == 0) mbar_expect_tx(&bars[bsel], (uint32_t)(nrows - nbad) * row_bytes);
     __syncthreads();
     for (int i = threadIdx.x; i < nrows; i += blockDim.x) {
       const int64_t r = r0 + i;
       const int64_t b = r / F;
       const int f = (int)(r - b * F);
       const krs_feature_t& ft = p.f[f];
-      const int64_t id = clamp_id(load_id<IdT>(ft.ids, b * ft.ids_stride), ft.vocab);
-      bulk_g2s(tile[bsel] + (size_t)i * E, ft.table + id * E, row_bytes, &bars[bsel]);
+      const int64_t id = resolve_id(load_id<IdT>(ft.ids, b * ft.ids_stride), ft.vocab);
+      if (id >= 0) {
+        bulk_g2s(tile[bsel] + (size_t)i * E, ft.table + id * E, row_bytes, &bars[bsel]);
+      } else {
+        for (int c = 0; c < E; ++c) tile[bsel][(size_t)i * E + c] = __int_as_float(0x7fc00000);
+      }
     }
+    if (nbad) __syncthreads();          // generic-proxy NaN rows are visible before thread 0's async-proxy fence
     mbar_wait(&bars[bsel], phase[bsel]);
     phase[bsel] ^= 1;
     if (threadIdx.x == 0) {
@@ -256,15 +278,17 @@ __global__ void __launch_bounds__(256) gather_generic_kernel(const __grid_consta
       for (int j = 0; j < W; ++j) acc[j] = 0.f;
       for (int h = 0; h < H; ++h) {
         const int64_t idx = b * ft.ids_stride + h;
-        const int64_t id = clamp_id(ft.ids_i64 ? load_id<int64_t>(ft.ids, idx) : load_id<int32_t>(ft.ids, idx), ft.vocab);
+        const int64_t id = resolve_id(ft.ids_i64 ? load_id<int64_t>(ft.ids, idx) : load_id<int32_t>(ft.ids, idx), ft.vocab);
         const float w = use_w ? ft.weights[idx] : 1.f;
-        const float* src = row_ptr(ft, id) + c * W;
         float v[W];
-        if (VEC) {
-          float4 t = ldg_nc_f4(src);
+        if (id < 0) {                        // no such row: NaN (jnp.take "fill"), which poisons the reduced sample
+#pragma unroll
+          for (int j = 0; j < W; ++j) v[j] = __int_as_float(0x7fc00000);
+        } else if (VEC) {
+          float4 t = ldg_nc_f4(row_ptr(ft, id) + c * W);
           v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
         } else {
-          v[0] = __ldg(src);
+          v[0] = __ldg(row_ptr(ft, id) + c * W);
         }
         // x = x * w ; sum over axis -2 in order h = 0..H-1 (no FMA contraction: embed_reduce.py:253,261)
 #pragma unroll
@@ -304,15 +328,11 @@ __global__ void __launch_bounds__(256) scatter_fast_kernel(const __grid_constant
     const int64_t b = b0 + lane;
     bool valid = b < p.B;
     int64_t id = -1 - lane;                              // unique negative sentinel for tail lanes
-    if (valid) id = clamp_id(load_id<IdT>(ft.ids, b * ft.ids_stride), ft.vocab);
-    int S = ft.num_shards;
-    if (S > 1 && (ft.shard_mode & 0xff) == KRS_SHARD_OWNER) {
-      // owner-side scatter of a peer's staged gradient rows: keep only the ids this rank owns and address
-      // the LOCAL arena by local row (all random traffic stays on this GPU)
-      if (valid && (int)(id % S) != ((ft.shard_mode >> 8) & 0xff)) { valid = false; id = -1 - lane; }
-      else if (valid) id = id / S;
-      S = 1;
+    if (valid) {
+      id = resolve_id(load_id<IdT>(ft.ids, b * ft.ids_stride), ft.vocab);
+      if (id < 0) { valid = false; id = -1 - lane; }        // ids that address no row receive no gradient
     }
+    const int S = ft.num_shards;
     const unsigned peers = __match_any_sync(0xffffffffu, id);
     const bool leader = valid && ((__ffs(peers) - 1) == lane);
     if (leader) {
@@ -367,41 +387,6 @@ __global__ void __launch_bounds__(256) scatter_fast_kernel(const __grid_constant
 }
 
 
-// ------------------------------------------------------------------ backward, positional push (KRS_SHARD_POSITION)
-// Row-sharded tables: every gradient row (b,f) is copied with plain 16-byte stores into the OWNER's staging
-// buffer at position b*F+f (shard_grads[id % S] + pos*E).  Remote addresses increase monotonically, so the NVLink
-// stream is sequential; the owner later scatter-adds its staged rows locally (KRS_SHARD_OWNER).
-template <int LPR, typename IdT>
-__global__ void __launch_bounds__(256) push_rows_kernel(const __grid_constant__ GatherParams p) {
-  constexpr int RPW = 32 / LPR;
-  constexpr int E = LPR * 4;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int sub = lane % LPR, rsub = lane / LPR;
-  const unsigned F = (unsigned)p.F;
-  const long long R = p.B * (long long)p.F;
-  const float* __restrict__ gout = p.out;
-  const long long r0 = ((long long)blockIdx.x * 8 + warp) * 32;
-  if (r0 >= R) return;
-  long long b = r0 / F;
-  unsigned f = (unsigned)(r0 - b * F) + lane;
-  while (f >= F) { f -= F; ++b; }
-  float* dst = nullptr;
-  if (r0 + lane < R) {
-    const krs_feature_t& ft = p.f[f];
-    const long long id = clamp_id(load_id<IdT>(ft.ids, b * ft.ids_stride), ft.vocab);
-    dst = ft.shard_grads[(int)(id % ft.num_shards)] + (r0 + lane) * E;
-  }
-#pragma unroll
-  for (int s0 = 0; s0 < LPR; ++s0) {
-    const int j = s0 * RPW + rsub;
-    float* q = reinterpret_cast<float*>(__shfl_sync(0xffffffffu, (unsigned long long)dst, j));
-    if (q) {
-      const float4 v = ldg_nc_f4(gout + (r0 + j) * E + sub * 4);
-      *reinterpret_cast<float4*>(q + sub * 4) = v;
-    }
-  }
-}
-
 // Generic: warp per (b,f) item, loops over hotness; coefficient = w / divisor.
 __global__ void __launch_bounds__(256) scatter_generic_kernel(const __grid_constant__ GatherParams p) {
   const int lane = threadIdx.x & 31;
@@ -427,9 +412,9 @@ __global__ void __launch_bounds__(256) scatter_generic_kernel(const __grid_const
     const float* g = gout + b * p.out_ld + ft.out_offset;
     for (int h = 0; h < H; ++h) {
       const int64_t idx = b * ft.ids_stride + h;
-      const int64_t id = clamp_id(ft.ids_i64 ? load_id<int64_t>(ft.ids, idx) : load_id<int32_t>(ft.ids, idx), ft.vocab);
+      const int64_t id = resolve_id(ft.ids_i64 ? load_id<int64_t>(ft.ids, idx) : load_id<int32_t>(ft.ids, idx), ft.vocab);
       const float coef = (use_w ? ft.weights[idx] : 1.f) * scale;
-      if (coef == 0.f) continue;
+      if (coef == 0.f || id < 0) continue;
       float* drow;
       if (ft.num_shards > 1) drow = ft.shard_grads[(int)(id % ft.num_shards)] + (id / ft.num_shards) * (int64_t)E;
       else drow = ft.grad + id * (int64_t)E;
@@ -457,10 +442,10 @@ int fill_params(GatherParams& p, const krs_feature_t* features, int F, int64_t B
     KRS_REQUIRE(f.dim > 0 && f.hotness > 0 && f.vocab > 0, "gather: feature %d has bad dim/hotness/vocab", i);
     KRS_REQUIRE(f.combiner >= 0 && f.combiner <= 2, "gather: feature %d has unknown combiner %d", i, f.combiner);
     KRS_REQUIRE(f.out_offset >= 0 && f.out_offset + f.dim <= out_ld, "gather: feature %d columns exceed out_ld", i);
-    KRS_REQUIRE(f.num_shards <= 1 || (f.shard_mode & 0xff) == KRS_SHARD_OWNER || f.shard_tables != nullptr ||
-                    f.shard_grads != nullptr,
+    KRS_REQUIRE(f.num_shards <= 1 || f.shard_tables != nullptr || f.shard_grads != nullptr,
                 "gather: feature %d is sharded but has no shard pointer array", i);
-    KRS_REQUIRE((f.shard_mode & 0xff) <= KRS_SHARD_POSITION, "gather: feature %d has an unknown shard_mode", i);
+    KRS_REQUIRE(f.num_shards <= 1 || (f.shard_mode & 0xff) == KRS_SHARD_DIRECT,
+                "gather: feature %d: only KRS_SHARD_DIRECT addressing exists here (the routed exchange is krs_xchg_*)", i);
     p.f[i] = f;
   }
   p.F = F;
@@ -479,7 +464,7 @@ bool uniform_onehot(const GatherParams& p, int* E_out, bool* i64, bool* sharded)
     if (f.hotness != 1 || f.dim != E || f.ids_i64 != is64 || ((f.num_shards > 1) != sh)) return false;
     if (f.weights != nullptr && (f.reduce || f.combiner == KRS_COMBINER_SUM)) return false;
     if (f.out_offset != i * E) return false;
-    if ((!sh || (f.shard_mode & 0xff) == KRS_SHARD_OWNER) && (f.table == nullptr || !aligned16(f.table))) return false;
+    if (!sh && (f.table == nullptr || !aligned16(f.table))) return false;
   }
   *sharded = sh;
   if (p.out_ld != (int64_t)p.F * E || !aligned16(p.out)) return false;
@@ -508,12 +493,8 @@ int launch_bulk(const GatherParams& p, int E, cudaStream_t s) {
   int tile_rows = (48 * 1024) / (E * 4);
   if (tile_rows < 1) return KRS_EUNSUPPORTED;
   const size_t smem = (size_t)2 * tile_rows * E * 4;
-  static bool attr_done = false;
-  if (!attr_done) {
-    KRS_CUDA(cudaFuncSetAttribute(gather_bulk_kernel<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    KRS_CUDA(cudaFuncSetAttribute(gather_bulk_kernel<int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_done = true;
-  }
+  // per device and cheap: set before every launch (a process may drive several GPUs)
+  KRS_CUDA(cudaFuncSetAttribute(gather_bulk_kernel<IdT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   const int64_t R = p.B * p.F;
   const int64_t ntiles = ceil_div<int64_t>(R, tile_rows);
   const unsigned grid = (unsigned)krs::imax<int64_t>(1, krs::imin<int64_t>(ntiles, (int64_t)sm_count() * 2));
@@ -534,11 +515,8 @@ extern "C" int krs_gather_fwd(const krs_feature_t* features, int F, int64_t B, f
   if (rc) return rc;
   KRS_REQUIRE(out != nullptr || B == 0, "krs_gather_fwd: null output");
   for (int i = 0; i < F; ++i) {
-    const bool needs_local = p.f[i].num_shards <= 1 || (p.f[i].shard_mode & 0xff) == KRS_SHARD_OWNER;
-    KRS_REQUIRE(needs_local ? p.f[i].table != nullptr : p.f[i].shard_tables != nullptr,
+    KRS_REQUIRE(p.f[i].num_shards <= 1 ? p.f[i].table != nullptr : p.f[i].shard_tables != nullptr,
                 "krs_gather_fwd: feature %d has no table", i);
-    KRS_REQUIRE(needs_local || variant != 3 || (p.f[i].shard_mode & 0xff) == KRS_SHARD_DIRECT,
-                "krs_gather_fwd: the generic path only addresses DIRECT sharded tables");
   }
   if (B == 0) return KRS_OK;
   cudaStream_t s = as_stream(stream);
@@ -600,38 +578,15 @@ extern "C" int krs_gather_bwd(const krs_feature_t* features, int F, int64_t B, c
   KRS_REQUIRE(gout != nullptr, "krs_gather_bwd: null gradient");
   bool fast = true;
   const int is64 = p.f[0].ids_i64;
-  const bool push = p.f[0].num_shards > 1 && (p.f[0].shard_mode & 0xff) == KRS_SHARD_POSITION;
   for (int i = 0; i < F; ++i) {
     const krs_feature_t& f = p.f[i];
-    const bool owner_mode = f.num_shards > 1 && (f.shard_mode & 0xff) == KRS_SHARD_OWNER;
-    KRS_REQUIRE((f.num_shards > 1 && !owner_mode) ? f.shard_grads != nullptr : f.grad != nullptr,
+    KRS_REQUIRE(f.num_shards > 1 ? f.shard_grads != nullptr : f.grad != nullptr,
                 "krs_gather_bwd: feature %d has no gradient arena", i);
-    KRS_REQUIRE(((f.num_shards > 1 && (f.shard_mode & 0xff) == KRS_SHARD_POSITION)) == push,
-                "krs_gather_bwd: positional push must be used for all features or none");
     if (f.hotness != 1 || f.ids_i64 != is64) fast = false;
     if (f.weights != nullptr && (f.reduce || f.combiner == KRS_COMBINER_SUM)) fast = false;
   }
   if (B == 0) return KRS_OK;
   cudaStream_t s = as_stream(stream);
-  if (push) {
-    const int E0 = p.f[0].dim;
-    bool ok = fast && (E0 % 4 == 0) && ((E0 / 4) & (E0 / 4 - 1)) == 0 && E0 <= 128 && aligned16(gout) && gout_ld == (int64_t)F * E0;
-    for (int i = 0; i < F && ok; ++i) ok = p.f[i].dim == E0 && p.f[i].out_offset == i * E0;
-    if (!ok) {
-      set_error("krs_gather_bwd: positional push needs 1-hot features of one dim E in {4..128} and a contiguous (B, F*E) gradient");
-      return KRS_EUNSUPPORTED;
-    }
-    const unsigned grid = (unsigned)ceil_div<int64_t>(ceil_div<int64_t>(B * F, 32), 8);
-#define KRS_PUSH(L)                                                                    \
-  case L:                                                                              \
-    if (is64) push_rows_kernel<L, int64_t><<<grid, 256, 0, s>>>(p);                    \
-    else push_rows_kernel<L, int32_t><<<grid, 256, 0, s>>>(p);                         \
-    break;
-    switch (E0 / 4) { KRS_PUSH(1) KRS_PUSH(2) KRS_PUSH(4) KRS_PUSH(8) KRS_PUSH(16) KRS_PUSH(32) }
-#undef KRS_PUSH
-    KRS_LAUNCH_CHECK();
-    return KRS_OK;
-  }
   if (fast) {
     const int64_t items = ceil_div<int64_t>(B, 32) * F;
     const unsigned grid = (unsigned)krs::imax<int64_t>(1, krs::imin<int64_t>(ceil_div<int64_t>(items, 8), 0x7fffffff));

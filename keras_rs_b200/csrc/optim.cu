@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(256) adamw_vec_kernel(float* __restrict__ p, f
                                                         float* __restrict__ v, float* __restrict__ g,
                                                         const uint32_t* __restrict__ touched,
                                                         const uint32_t* __restrict__ ever,
-                                                        const uint32_t* __restrict__ skip, int64_t n4, int row_len4,
+                                                        int64_t n4, int row_len4,
                                                         AdamArgs a, const float* __restrict__ hyper) {
   if (hyper) { a.lr = hyper[0]; a.b1 = hyper[1]; a.b2 = hyper[2]; a.eps = hyper[3]; a.wd = hyper[4]; a.alpha = hyper[5]; }
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -46,7 +46,6 @@ __global__ void __launch_bounds__(256) adamw_vec_kernel(float* __restrict__ p, f
     bool hit = !ARENA;
     if (ARENA) {
       const int64_t row = i / row_len4;
-      if (skip != nullptr && ((skip[row >> 5] >> (row & 31)) & 1u)) continue;     // already updated by krs_adamw_rows
       hit = (touched[row >> 5] >> (row & 31)) & 1u;
       if (ever != nullptr && !hit && !((ever[row >> 5] >> (row & 31)) & 1u)) {     // cold row: decay only
         float4 pc = reinterpret_cast<float4*>(p)[i];
@@ -152,35 +151,95 @@ __global__ void __launch_bounds__(256) dense_sgd_adagrad_kernel(float* __restric
   }
 }
 
-// Hot rows of a pipelined AdamW step: the rows the NEXT batch will gather get their update first (one warp per lookup;
-// the lane that flips the row's bit in `pre` owns the row, duplicates skip), the rest of the table is swept later by
-// adamw_vec_kernel with skip = pre, possibly on another stream under the next step's forward / backward.
-struct RowOffsets { int64_t off[64]; };
-__global__ void __launch_bounds__(256) adamw_rows_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
-                                                         float* __restrict__ g, const uint32_t* __restrict__ touched,
-                                                         uint32_t* __restrict__ pre, const int32_t* __restrict__ ids,
-                                                         const RowOffsets ro, int64_t n_lookups, int F, int E, AdamArgs a) {
-  const int lane = threadIdx.x & 31;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t idx = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; idx < n_lookups; idx += nwarps) {
-    const int f = (int)(idx % F);
-    const int64_t row = ro.off[f] + (int64_t)ids[idx];
-    const uint32_t bit = 1u << (row & 31);
-    uint32_t old = 0;
-    if (lane == 0) old = atomicOr(&pre[row >> 5], bit);
-    old = __shfl_sync(0xffffffffu, old, 0);
-    if (old & bit) continue;                                   // another lookup of the same row owns it
-    const bool hit = (touched[row >> 5] >> (row & 31)) & 1u;
-    const int64_t base = row * (int64_t)E;
-    for (int c = lane; c < E; c += 32) {
-      const float gg = hit ? g[base + c] : 0.f;
-      float pp = p[base + c], mm = m[base + c], vv = v[base + c];
-      adamw_one(pp, mm, vv, gg, a);
-      p[base + c] = pp;
-      m[base + c] = mm;
-      v[base + c] = vv;
-      if (hit) g[base + c] = 0.f;
+// ------------------------------------------------------------------ optimizers on COMPACT gradient rows
+// The row-sharded backward (exchange.cu) leaves one gradient row per distinct touched table row in `compact`
+// (slot order = arena row order) plus uniq_rows[slot]; nothing table-sized exists besides the table and its slots.
+struct RowsHyper { float h[8]; };
+
+template <int KIND>
+__device__ __forceinline__ void rows_update_one(float& p, float& s1, float& s2, float g, const RowsHyper& H) {
+  if (KIND == KRS_OPT_SGD) {
+    p = p - H.h[0] * g;
+  } else if (KIND == KRS_OPT_ADAGRAD) {            // keras Adagrad: acc += g^2 ; p -= lr * g / sqrt(acc + eps)
+    s1 = s1 + g * g;
+    p = p - H.h[0] * g / sqrtf(s1 + H.h[1]);
+  } else if (KIND == KRS_OPT_ADAM) {               // keras Adam on the touched rows only (lazy / SparseCore form)
+    s1 = s1 + (g - s1) * (1.f - H.h[1]);
+    s2 = s2 + (g * g - s2) * (1.f - H.h[2]);
+    p = p - (s1 * H.h[4]) / (sqrtf(s2) + H.h[3]);
+  } else {                                         // keras Ftrl (l2_shrinkage = 0, the only form the reference accepts)
+    const float lr = H.h[0], lrp = H.h[1], l1 = H.h[2], l2 = H.h[3] + H.h[4] / (2.f * lr);
+    const float na = s1 + g * g;
+    const float pa = (lrp == -0.5f) ? sqrtf(s1) : powf(s1, -lrp);
+    const float pn = (lrp == -0.5f) ? sqrtf(na) : powf(na, -lrp);
+    s2 = s2 + (g - (pn - pa) / lr * p);
+    const float quad = pn / lr + 2.f * l2;
+    const float lc = fminf(fmaxf(s2, -l1), l1);
+    p = (lc - s2) / quad;
+    s1 = na;
+  }
+}
+
+// LPR lanes per compact row (float4 each per pass): slots are consecutive, table rows increase with the slot.
+template <int KIND>
+__global__ void __launch_bounds__(256) rows_apply_kernel(float* __restrict__ p, float* __restrict__ s1,
+                                                         float* __restrict__ s2, float* __restrict__ compact,
+                                                         const int32_t* __restrict__ uniq_rows,
+                                                         const uint32_t* __restrict__ n_unique, int64_t cap_rows, int E4,
+                                                         int lpr, const RowsHyper H) {
+  const int64_t n = krs::imin<int64_t>((int64_t)*n_unique, cap_rows);
+  const int sub = threadIdx.x % lpr;
+  const int64_t ngroups = ((int64_t)gridDim.x * blockDim.x) / lpr;
+  for (int64_t slot = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / lpr; slot < n; slot += ngroups) {
+    const int64_t row = uniq_rows[slot];
+    for (int c = sub; c < E4; c += lpr) {
+      const int64_t gi = slot * E4 + c, pi = row * E4 + c;
+      const float4 g = reinterpret_cast<const float4*>(compact)[gi];
+      float4 pp = reinterpret_cast<float4*>(p)[pi];
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+      if (KIND != KRS_OPT_SGD) a = reinterpret_cast<float4*>(s1)[pi];
+      if (KIND == KRS_OPT_ADAM || KIND == KRS_OPT_FTRL) b = reinterpret_cast<float4*>(s2)[pi];
+      rows_update_one<KIND>(pp.x, a.x, b.x, g.x, H);
+      rows_update_one<KIND>(pp.y, a.y, b.y, g.y, H);
+      rows_update_one<KIND>(pp.z, a.z, b.z, g.z, H);
+      rows_update_one<KIND>(pp.w, a.w, b.w, g.w, H);
+      reinterpret_cast<float4*>(p)[pi] = pp;
+      if (KIND != KRS_OPT_SGD) reinterpret_cast<float4*>(s1)[pi] = a;
+      if (KIND == KRS_OPT_ADAM || KIND == KRS_OPT_FTRL) reinterpret_cast<float4*>(s2)[pi] = b;
+      reinterpret_cast<float4*>(compact)[gi] = make_float4(0.f, 0.f, 0.f, 0.f);      // loads first, re-zeroing store last
     }
+  }
+}
+
+// adamw_vec_kernel<ARENA> with the gradient row fetched through the slot numbering of the touched bitmap.
+__global__ void __launch_bounds__(256) adamw_compact_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
+                                                            float* __restrict__ compact, const uint32_t* __restrict__ touched,
+                                                            const uint32_t* __restrict__ wordprefix,
+                                                            const uint32_t* __restrict__ blockbase, int64_t n4, int row_len4,
+                                                            AdamArgs a) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / row_len4;
+    const uint32_t word = touched[row >> 5];
+    const bool hit = (word >> (row & 31)) & 1u;
+    int64_t gi = 0;
+    float4 gp = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (hit) {
+      const int64_t w = row >> 5;
+      const int64_t slot = (int64_t)blockbase[w >> 10] + wordprefix[w] + __popc(word & ((1u << (row & 31)) - 1u));
+      gi = slot * row_len4 + (i - row * row_len4);
+      gp = reinterpret_cast<const float4*>(compact)[gi];
+    }
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    adamw_one(pp.x, mm.x, vv.x, gp.x, a);
+    adamw_one(pp.y, mm.y, vv.y, gp.y, a);
+    adamw_one(pp.z, mm.z, vv.z, gp.z, a);
+    adamw_one(pp.w, mm.w, vv.w, gp.w, a);
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+    if (hit) reinterpret_cast<float4*>(compact)[gi] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 
@@ -216,38 +275,10 @@ extern "C" int krs_adamw(float* p, float* m, float* v, float* g, uint32_t* touch
   return krs_adamw_cold(p, m, v, g, touched, nullptr, n, row_len, lr, b1, b2, eps, wd, step, hyper_dev, stream);
 }
 
-extern "C" int krs_adamw_skip(float* p, float* m, float* v, float* g, uint32_t* touched, uint32_t* ever, uint32_t* skip,
-                              int64_t n, int row_len, float lr, float b1, float b2, float eps, float wd, int64_t step,
-                              const float* hyper_dev, void* stream);
 extern "C" int krs_adamw_cold(float* p, float* m, float* v, float* g, uint32_t* touched, uint32_t* ever, int64_t n, int row_len,
                               float lr, float b1, float b2, float eps, float wd, int64_t step, const float* hyper_dev,
                               void* stream) {
-  return krs_adamw_skip(p, m, v, g, touched, ever, nullptr, n, row_len, lr, b1, b2, eps, wd, step, hyper_dev, stream);
-}
-
-extern "C" int krs_adamw_rows(float* p, float* m, float* v, float* g, const uint32_t* touched, uint32_t* pre,
-                              const int32_t* ids, const int64_t* row_off, int64_t B, int F, int E, float lr, float b1, float b2,
-                              float eps, float wd, int64_t step, void* stream) {
-  KRS_REQUIRE(p && m && v && g && touched && pre && ids && row_off, "krs_adamw_rows: null argument");
-  KRS_REQUIRE(F >= 1 && F <= 64 && E >= 1 && B >= 0 && step >= 1, "krs_adamw_rows: bad F/E/B/step");
-  if (B == 0) return KRS_OK;
-  RowOffsets ro;
-  for (int f = 0; f < F; ++f) ro.off[f] = row_off[f];
-  AdamArgs a;
-  a.lr = lr; a.b1 = b1; a.b2 = b2; a.eps = eps; a.wd = wd;
-  a.alpha = (float)((double)lr * sqrt(1.0 - pow((double)b2, (double)step)) / (1.0 - pow((double)b1, (double)step)));
-  const int64_t n_lookups = B * (int64_t)F;
-  const unsigned grid = (unsigned)krs::imax<int64_t>(1, krs::imin<int64_t>(ceil_div<int64_t>(n_lookups, 8), (int64_t)sm_count() * 32));
-  adamw_rows_kernel<<<grid, 256, 0, as_stream(stream)>>>(p, m, v, g, touched, pre, ids, ro, n_lookups, F, E, a);
-  KRS_LAUNCH_CHECK();
-  return KRS_OK;
-}
-
-extern "C" int krs_adamw_skip(float* p, float* m, float* v, float* g, uint32_t* touched, uint32_t* ever, uint32_t* skip,
-                              int64_t n, int row_len, float lr, float b1, float b2, float eps, float wd, int64_t step,
-                              const float* hyper_dev, void* stream) {
   KRS_REQUIRE(p && m && v && g, "krs_adamw: null argument");
-  KRS_REQUIRE(skip == nullptr || touched != nullptr, "krs_adamw_skip: the skip bitmap needs the gradient arena");
   KRS_REQUIRE(ever == nullptr || touched != nullptr, "krs_adamw_cold: the ever-touched bitmap needs the gradient arena");
   KRS_REQUIRE(n >= 0 && (step >= 1 || hyper_dev != nullptr), "krs_adamw: bad n/step");
   KRS_REQUIRE(touched == nullptr || (row_len > 0 && n % row_len == 0), "krs_adamw: arena needs n %% row_len == 0");
@@ -259,12 +290,11 @@ extern "C" int krs_adamw_skip(float* p, float* m, float* v, float* g, uint32_t* 
                       : (float)((double)lr * sqrt(1.0 - pow((double)b2, (double)step)) / (1.0 - pow((double)b1, (double)step)));
   const bool vec = (n % 4 == 0) && aligned16(p) && aligned16(m) && aligned16(v) && aligned16(g) &&
                    (touched == nullptr || row_len % 4 == 0);
-  KRS_REQUIRE(skip == nullptr || vec, "krs_adamw_skip: the skip bitmap needs the vector path (n %% 4 == 0, row_len %% 4 == 0, 16-byte aligned)");
   const int64_t work = vec ? n / 4 : n;
   const unsigned grid = (unsigned)krs::imax<int64_t>(1, krs::imin<int64_t>(ceil_div<int64_t>(work, 256), (int64_t)sm_count() * 32));
   if (vec) {
-    if (touched) adamw_vec_kernel<true><<<grid, 256, 0, s>>>(p, m, v, g, touched, ever, skip, work, row_len / 4, a, hyper_dev);
-    else adamw_vec_kernel<false><<<grid, 256, 0, s>>>(p, m, v, g, nullptr, nullptr, nullptr, work, 1, a, hyper_dev);
+    if (touched) adamw_vec_kernel<true><<<grid, 256, 0, s>>>(p, m, v, g, touched, ever, work, row_len / 4, a, hyper_dev);
+    else adamw_vec_kernel<false><<<grid, 256, 0, s>>>(p, m, v, g, nullptr, nullptr, work, 1, a, hyper_dev);
   } else {
     if (touched) adamw_scalar_kernel<true><<<grid, 256, 0, s>>>(p, m, v, g, touched, n, row_len, a, hyper_dev);
     else adamw_scalar_kernel<false><<<grid, 256, 0, s>>>(p, m, v, g, nullptr, n, 1, a, hyper_dev);
@@ -280,7 +310,6 @@ extern "C" int krs_adamw_skip(float* p, float* m, float* v, float* g, uint32_t* 
     } else {
       KRS_CUDA(cudaMemsetAsync(touched, 0, sizeof(uint32_t) * (size_t)nwords, s));
     }
-    if (skip != nullptr) KRS_CUDA(cudaMemsetAsync(skip, 0, sizeof(uint32_t) * (size_t)nwords, s));
   }
   return KRS_OK;
 }
@@ -310,5 +339,53 @@ extern "C" int krs_adam_hyper_advance(float* hyper_dev, void* stream) {
   KRS_REQUIRE(hyper_dev != nullptr, "krs_adam_hyper_advance: null argument");
   adam_hyper_advance_kernel<<<1, 1, 0, as_stream(stream)>>>(hyper_dev);
   KRS_LAUNCH_CHECK();
+  return KRS_OK;
+}
+
+extern "C" int krs_rows_apply(float* p, float* s1, float* s2, float* compact, const int32_t* uniq_rows, const uint32_t* n_unique,
+                              int64_t cap_rows, int E, int kind, const float* hyper, uint32_t* touched_to_clear, int64_t nwords,
+                              void* stream) {
+  KRS_REQUIRE(p && compact && uniq_rows && n_unique && hyper, "krs_rows_apply: null argument");
+  KRS_REQUIRE(kind >= KRS_OPT_SGD && kind <= KRS_OPT_FTRL, "krs_rows_apply: unknown optimizer kind %d", kind);
+  KRS_REQUIRE(kind == KRS_OPT_SGD || s1 != nullptr, "krs_rows_apply: optimizer kind %d needs its first slot variable", kind);
+  KRS_REQUIRE((kind != KRS_OPT_ADAM && kind != KRS_OPT_FTRL) || s2 != nullptr, "krs_rows_apply: optimizer kind %d needs two slot variables", kind);
+  KRS_REQUIRE(E >= 4 && E % 4 == 0 && aligned16(p) && aligned16(compact) && (s1 == nullptr || aligned16(s1)) &&
+                  (s2 == nullptr || aligned16(s2)),
+              "krs_rows_apply: rows must be 16-byte aligned multiples of 4 floats");
+  KRS_REQUIRE(cap_rows > 0, "krs_rows_apply: cap_rows must be positive");
+  RowsHyper H;
+  for (int i = 0; i < 8; ++i) H.h[i] = hyper[i];
+  int lpr = 1;
+  while (lpr < E / 4 && lpr < 32) lpr <<= 1;
+  // the number of distinct rows lives on the device: size the grid for the capacity, capped at a few waves
+  const int64_t groups_per_cta = 256 / lpr;
+  const unsigned grid = (unsigned)krs::imax<int64_t>(1, krs::imin<int64_t>(ceil_div<int64_t>(cap_rows, groups_per_cta), (int64_t)sm_count() * 16));
+  cudaStream_t s = as_stream(stream);
+  switch (kind) {
+    case KRS_OPT_SGD: rows_apply_kernel<KRS_OPT_SGD><<<grid, 256, 0, s>>>(p, s1, s2, compact, uniq_rows, n_unique, cap_rows, E / 4, lpr, H); break;
+    case KRS_OPT_ADAGRAD: rows_apply_kernel<KRS_OPT_ADAGRAD><<<grid, 256, 0, s>>>(p, s1, s2, compact, uniq_rows, n_unique, cap_rows, E / 4, lpr, H); break;
+    case KRS_OPT_ADAM: rows_apply_kernel<KRS_OPT_ADAM><<<grid, 256, 0, s>>>(p, s1, s2, compact, uniq_rows, n_unique, cap_rows, E / 4, lpr, H); break;
+    default: rows_apply_kernel<KRS_OPT_FTRL><<<grid, 256, 0, s>>>(p, s1, s2, compact, uniq_rows, n_unique, cap_rows, E / 4, lpr, H); break;
+  }
+  KRS_LAUNCH_CHECK();
+  if (touched_to_clear != nullptr && nwords > 0) KRS_CUDA(cudaMemsetAsync(touched_to_clear, 0, sizeof(uint32_t) * (size_t)nwords, s));
+  return KRS_OK;
+}
+
+extern "C" int krs_adamw_compact(float* p, float* m, float* v, float* compact, uint32_t* touched, const uint32_t* wordprefix,
+                                 const uint32_t* blockbase, int64_t n, int row_len, float lr, float b1, float b2, float eps,
+                                 float wd, int64_t step, void* stream) {
+  KRS_REQUIRE(p && m && v && compact && touched && wordprefix && blockbase, "krs_adamw_compact: null argument");
+  KRS_REQUIRE(n >= 0 && step >= 1 && row_len >= 4 && row_len % 4 == 0 && n % row_len == 0, "krs_adamw_compact: bad n / row_len / step");
+  KRS_REQUIRE(aligned16(p) && aligned16(m) && aligned16(v) && aligned16(compact), "krs_adamw_compact: buffers must be 16-byte aligned");
+  if (n == 0) return KRS_OK;
+  AdamArgs a;
+  a.lr = lr; a.b1 = b1; a.b2 = b2; a.eps = eps; a.wd = wd;
+  a.alpha = (float)((double)lr * sqrt(1.0 - pow((double)b2, (double)step)) / (1.0 - pow((double)b1, (double)step)));
+  const int64_t work = n / 4;
+  const unsigned grid = (unsigned)krs::imax<int64_t>(1, krs::imin<int64_t>(ceil_div<int64_t>(work, 256), (int64_t)sm_count() * 32));
+  adamw_compact_kernel<<<grid, 256, 0, as_stream(stream)>>>(p, m, v, compact, touched, wordprefix, blockbase, work, row_len / 4, a);
+  KRS_LAUNCH_CHECK();
+  KRS_CUDA(cudaMemsetAsync(touched, 0, sizeof(uint32_t) * (size_t)ceil_div<int64_t>(n / row_len, 32), as_stream(stream)));
   return KRS_OK;
 }

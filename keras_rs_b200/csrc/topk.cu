@@ -15,7 +15,6 @@
 // (jax.lax.top_k rule adopted in SURVEY.md Appendix A.3), independent of thread scheduling.
 #include <limits.h>
 #include <math.h>
-#include <stdlib.h>
 
 #include <atomic>
 
@@ -264,36 +263,18 @@ __device__ __forceinline__ int score_key(float x) {
 }
 __device__ __forceinline__ float key_score(int key) { return __int_as_float(key >= 0 ? key : (key ^ 0x7fffffff)); }
 
-// Tile order inside a slice.  The q_tiles CTAs that stream the same slice run in near lockstep; in plain order they all
-// ask for the same candidate tile at the same moment, the requests merge into ONE DRAM fetch and EVERY CTA waits out the
-// DRAM latency (ncu: the converters polled the TMA barrier ~70 times per ring entry; 10 ring entries cannot cover it).
-// Windows of `win` tiles are therefore walked with a per-query-tile rotation: each CTA first-touches its own 1/q_tiles of
-// the window and finds the rest already in L2, fetched moments earlier by its neighbours (the window of every concurrently
-// running slice fits in L2).
-__device__ __forceinline__ int64_t slice_tile(int64_t t0, int64_t nt, int64_t j, int win, int qt, int q_tiles) {
-  if (win <= 0) return t0 + j;
-  const int64_t w0 = (j / win) * win;
-  const int64_t wl = imin<int64_t>((int64_t)win, nt - w0);
-  const int64_t r = ((int64_t)qt * wl) / q_tiles;
-  return t0 + w0 + ((j - w0 + r) % wl);
-}
-
 struct TopkTcArgs {
   float* part_s;
   int32_t* part_i;
   int* g_bound;          // [nq] best k-th score any slice has reached so far (score_key), a lower bound of the final k-th
   int64_t nq, nc;
   int d, k, S, KB, stages;
-  int c_lo_tma;          // the candidates' lo plane is precomputed (krs_topk_split_candidates) and streamed by TMA:
-                         // candidate entries skip the converters entirely (TMA -> UMMA)
   int q_tiles;
-  int win;               // rotation window in tiles (0 = plain order)
   int64_t tiles_per_slice, ntiles, n_items;
 };
 
 __global__ void __launch_bounds__(T_THREADS, 1)
-topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
-               const __grid_constant__ CUtensorMap tmap_clo, const TopkTcArgs a) {
+topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c, const TopkTcArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int STAGES = a.stages;
@@ -306,9 +287,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   uint64_t* tmem_full = bars + 3 * T_MAX_STAGES;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;            // [2]
   uint64_t* qfree_bar = tmem_empty + 2;            // [1] all MMAs of the item have completed (query columns reusable)
-  uint64_t* qconv_bar = qfree_bar + 1;             // [T_MAXKB] c_lo_tma mode: query k-block parked in TMEM (once per item; the
-                                                   // per-stage conv_bar would not complete on laps where the stage holds a candidate entry)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(qconv_bar + T_MAXKB);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(qfree_bar + 1);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -323,7 +302,6 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       mbar_init(&tmem_empty[i], 4);
     }
     mbar_init(qfree_bar, 1);
-    for (int i = 0; i < T_MAXKB; ++i) mbar_init(&qconv_bar[i], 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 13) {
@@ -353,19 +331,15 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         }
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      for (int64_t j = 0; j < t1 - t0; ++j) {
-        const int64_t tile = slice_tile(t0, t1 - t0, j, a.win, qt, a.q_tiles);
+      for (int64_t tile = t0; tile < t1; ++tile)
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait_uniform(&empty_bar[stage], phase ^ 1);
           if (elect_one()) {
-            mbar_expect_tx(&full_bar[stage], (uint32_t)(a.c_lo_tma ? 2 * T_CBYTES : T_CBYTES));
+            mbar_expect_tx(&full_bar[stage], (uint32_t)T_CBYTES);
             tma_load_2d(smem + (size_t)stage * T_STAGE, &tmap_c, kb * TKB, (int)(tile * TNC), &full_bar[stage]);
-            if (a.c_lo_tma)
-              tma_load_2d(smem + (size_t)stage * T_STAGE + T_CBYTES, &tmap_clo, kb * TKB, (int)(tile * TNC), &full_bar[stage]);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-      }
     }
   } else if (warp == 13) {
     // ======================= MMA issuer =======================
@@ -376,15 +350,13 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    uint32_t items_done = 0;
     for (int64_t item = blockIdx.x; item < a.n_items; item += gridDim.x) {
       const int64_t sl = item / a.q_tiles;
       const int64_t t0 = sl * a.tiles_per_slice;
       const int64_t t1 = imin<int64_t>(a.ntiles, t0 + a.tiles_per_slice);
       // query entries: nothing to multiply, the entry is released as soon as the converters have parked it in TMEM
       for (int kb = 0; kb < KB; ++kb) {
-        if (a.c_lo_tma) mbar_wait_uniform(&qconv_bar[kb], items_done & 1u);
-        else mbar_wait_uniform(&conv_bar[stage], phase);
+        mbar_wait_uniform(&conv_bar[stage], phase);
         tc_fence_after();
         if (elect_one()) tc_commit(&empty_bar[stage]);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -395,7 +367,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         const uint32_t d_main = tmem_base + (uint32_t)(acc * 2 * TNC);
         const uint32_t d_cross = d_main + (uint32_t)TNC;
         for (int kb = 0; kb < KB; ++kb) {
-          mbar_wait_uniform(a.c_lo_tma ? &full_bar[stage] : &conv_bar[stage], phase);
+          mbar_wait_uniform(&conv_bar[stage], phase);
           tc_fence_after();
           if (elect_one()) {
             const uint32_t so = (uint32_t)(stage * T_STAGE) >> 4;
@@ -416,7 +388,6 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
       if (elect_one()) tc_commit(qfree_bar);      // completes when every MMA of this item has retired
-      ++items_done;
     }
   } else if (warp >= 4 && warp < 12) {
     // ======================= converters =======================
@@ -459,19 +430,11 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           tc_wait_st();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(a.c_lo_tma ? &qconv_bar[kb] : &conv_bar[stage]);
+          if (lane == 0) mbar_arrive(&conv_bar[stage]);
         }
         ++cnt;
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      if (a.c_lo_tma) {
-        // candidate entries go TMA -> UMMA: only advance the ring position past them
-        const int64_t n_entries = (t1 > t0 ? (t1 - t0) : 0) * KB;
-        const int64_t pos = (int64_t)stage + n_entries;
-        phase ^= (uint32_t)((pos / STAGES) & 1);
-        stage = (int)(pos % STAGES);
-        cnt += (uint32_t)(n_entries & 1);
-      } else
       for (int64_t tile = t0; tile < t1; ++tile)
         for (int kb = 0; kb < KB; ++kb) {
           if ((int)(cnt & 1u) == grp) {
@@ -521,8 +484,7 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       float th = -INFINITY;
       const int64_t q_me = (int64_t)qt * TQ + warp * 32 + lane;
       int published = INT_MIN;
-      for (int64_t j = 0; j < t1 - t0; ++j) {
-        const int64_t tile = slice_tile(t0, t1 - t0, j, a.win, qt, a.q_tiles);
+      for (int64_t tile = t0; tile < t1; ++tile) {
         if (q_me < a.nq) th = fmaxf(th, key_score(*reinterpret_cast<volatile int*>(a.g_bound + q_me)));
         mbar_wait_relaxed(&tmem_full[acc], acc_phase);
         tc_fence_after();
@@ -622,19 +584,6 @@ topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   }
 }
 
-// lo plane of the candidate matrix: C_lo = tf32_rn(C - trunc_tf32(C)), bit-identical to the in-kernel converters
-__global__ void __launch_bounds__(256) topk_split_lo_kernel(const float4* __restrict__ src, float4* __restrict__ dst, int64_t nvec) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
-    const float4 x = ldg_nc_f4(reinterpret_cast<const float*>(src + i));
-    float4 l;
-    l.x = tf32_lo_of(x.x);
-    l.y = tf32_lo_of(x.y);
-    l.z = tf32_lo_of(x.z);
-    l.w = tf32_lo_of(x.w);
-    stg_cs_f4(reinterpret_cast<float*>(dst + i), l);
-  }
-}
-
 std::atomic<int> g_topk_engine{0};        // 0 auto, 1 FFMA tiles only, 2 tensor pipe whenever eligible
 std::atomic<long long> g_topk_tc_launches{0};
 
@@ -716,27 +665,8 @@ extern "C" size_t krs_topk_workspace_bytes(int64_t nq, int64_t nc, int d, int k)
   return (size_t)nq * S * k * (sizeof(float) + sizeof(int32_t)) + (p.ok ? (size_t)nq * sizeof(int) : 0);
 }
 
-extern "C" int krs_topk_split_candidates(const float* C, float* C_lo, int64_t nc, int d, void* stream) {
-  KRS_REQUIRE(C && C_lo && nc > 0 && d > 0, "krs_topk_split_candidates: bad argument");
-  KRS_REQUIRE(aligned16(C) && aligned16(C_lo) && ((nc * d) & 3) == 0, "krs_topk_split_candidates: 16-byte aligned planes of a multiple of 4 floats");
-  const int64_t nvec = nc * d / 4;
-  const unsigned grid = (unsigned)imax<int64_t>(1, imin<int64_t>(ceil_div<int64_t>(nvec, 256), (int64_t)sm_count() * 16));
-  topk_split_lo_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(C), reinterpret_cast<float4*>(C_lo), nvec);
-  KRS_LAUNCH_CHECK();
-  return KRS_OK;
-}
-
-extern "C" int krs_topk_lo(const float* Q, const float* C, const float* C_lo, const int32_t* cand_ids, float* top_scores,
-                           int32_t* top_ids, int64_t nq, int64_t nc, int d, int k, void* workspace, size_t workspace_bytes,
-                           void* stream);
 extern "C" int krs_topk(const float* Q, const float* C, const int32_t* cand_ids, float* top_scores, int32_t* top_ids,
                         int64_t nq, int64_t nc, int d, int k, void* workspace, size_t workspace_bytes, void* stream) {
-  return krs_topk_lo(Q, C, nullptr, cand_ids, top_scores, top_ids, nq, nc, d, k, workspace, workspace_bytes, stream);
-}
-
-extern "C" int krs_topk_lo(const float* Q, const float* C, const float* C_lo, const int32_t* cand_ids, float* top_scores,
-                           int32_t* top_ids, int64_t nq, int64_t nc, int d, int k, void* workspace, size_t workspace_bytes,
-                           void* stream) {
   KRS_REQUIRE(Q && C && top_ids, "krs_topk: null argument");
   KRS_REQUIRE(nq >= 0 && nc > 0 && d > 0, "krs_topk: bad shape");
   KRS_REQUIRE(k >= 1 && k <= KP, "krs_topk: k must be in 1..%d, got %d", KP, k);
@@ -750,22 +680,10 @@ extern "C" int krs_topk_lo(const float* Q, const float* C, const float* C_lo, co
   if (use_tc(tp, nq, nc) && aligned16(Q) && aligned16(C)) {
     const size_t need_tc = (size_t)nq * tp.S * k * (sizeof(float) + sizeof(int32_t)) + (size_t)nq * sizeof(int);
     KRS_REQUIRE(workspace && workspace_bytes >= need_tc, "krs_topk: workspace too small (%zu < %zu)", workspace_bytes, need_tc);
-    CUtensorMap mq, mc, mclo;
-    const bool have_lo = C_lo != nullptr && aligned16(C_lo);
+    CUtensorMap mq, mc;
     if (make_map(&mq, Q, nq, d, d, TKB, TQ, CU_TENSOR_MAP_SWIZZLE_64B) &&
-        make_map(&mc, C, nc, d, d, TKB, TNC, CU_TENSOR_MAP_SWIZZLE_64B) &&
-        make_map(&mclo, have_lo ? C_lo : C, nc, d, d, TKB, TNC, CU_TENSOR_MAP_SWIZZLE_64B)) {
+        make_map(&mc, C, nc, d, d, TKB, TNC, CU_TENSOR_MAP_SWIZZLE_64B)) {
       TopkTcArgs t;
-      t.c_lo_tma = have_lo ? 1 : 0;
-      {
-        // window ~8 MB of candidate bytes (both planes when the lo plane is streamed): q_tiles CTAs x (SMs / q_tiles)
-        // concurrent slices keep well under the 126 MB L2
-        const int64_t tile_bytes = (int64_t)TNC * d * 4 * (have_lo ? 2 : 1);
-        int64_t win = ((int64_t)8 << 20) / tile_bytes;
-        if (win < 4 * (int64_t)tp.q_tiles) win = 4 * (int64_t)tp.q_tiles;     // at least a few first-touch tiles per CTA
-        t.win = tp.q_tiles > 1 ? (int)imin<int64_t>(win, 1 << 20) : 0;
-        if (const char* e = getenv("KRS_TOPK_WIN")) t.win = atoi(e);
-      }
       t.part_s = reinterpret_cast<float*>(workspace);
       t.part_i = reinterpret_cast<int32_t*>(t.part_s + (size_t)nq * tp.S * k);
       t.g_bound = reinterpret_cast<int*>(t.part_i + (size_t)nq * tp.S * k);
@@ -774,7 +692,7 @@ extern "C" int krs_topk_lo(const float* Q, const float* C, const float* C_lo, co
       t.q_tiles = tp.q_tiles; t.tiles_per_slice = tp.tiles_per_slice; t.ntiles = tp.ntiles; t.n_items = tp.n_items;
       KRS_CUDA(cudaFuncSetAttribute(topk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       const unsigned grid = (unsigned)imax<int64_t>(1, imin<int64_t>(tp.n_items, sm_count()));
-      topk_tc_kernel<<<grid, T_THREADS, tp.smem, s>>>(mq, mc, mclo, t);
+      topk_tc_kernel<<<grid, T_THREADS, tp.smem, s>>>(mq, mc, t);
       KRS_LAUNCH_CHECK();
       g_topk_tc_launches.fetch_add(1);
       int P = 1;

@@ -203,9 +203,17 @@ class DCN(torch.nn.Module):
     def _run_step(self, b, B: int, denom: int = 0):
         """Forward + backward on the staged batch (ids / labels already in the static buffers)."""
         s = stream()
+        self._gather_into(b, B, s)
+        cur = self._dense_step(b, B, denom, s)
+        # cur holds dL/dx0 (B, D): scatter-add into the embedding arena
+        self._scatter_from(b, B, cur, s)
+        return b["loss"]
+
+    def _dense_step(self, b, B: int, denom: int, s):
+        """Everything between the gather and the scatter: cross stack, MLP, loss and their backward.  Returns the
+        buffer (ga or gb) that holds dL/dx0."""
         D, P = self.D, (self.P or 0)
         xs = b["xs"]
-        self._gather_into(b, B, s)
         for i, c in enumerate(self.cross):
             x_in = xs[0] if i == 0 else xs[i]
             check(lib.krs_cross_fwd(ptr(xs[0]), ptr(x_in), ptr(c.down_proj_kernel), ptr(c.kernel), ptr(c.bias),
@@ -245,11 +253,7 @@ class DCN(torch.nn.Module):
                                     ptr(self._g(c.kernel)), ptr(self._g(c.bias)) if c.bias is not None else None,
                                     ptr(b["dz"]), ptr(b["dh"]), B, D, P, flags, s))
             cur, nxt = nxt, cur
-        if self.L == 0:
-            pass
-        # cur holds dL/dx0 (B, D): scatter-add into the embedding arena
-        self._scatter_from(b, B, cur, s)
-        return b["loss"]
+        return cur
 
     def _gather_into(self, b, B, s):
         """Fused multi-table gather of the staged ids into xs[0] (overridden by the row-sharded model)."""
@@ -262,15 +266,18 @@ class DCN(torch.nn.Module):
 
     def train_on_batch(self, ids, labels, optimizer: optimizers.Optimizer, denom: int = 0):
         loss = self.forward_backward(ids, labels, denom)
-        self._sync_gradients()
         optimizer.iterations += 1
         if getattr(optimizer, "_hyper_dev", None) is not None:
             optimizer.advance_device_hyper()       # keep the device-resident step / alpha in lock-step
         with torch.no_grad():
-            optimizer._update(self.emb, self.emb_grad, self.emb_touched)
+            self._update_tables(optimizer)
+            self._sync_gradients()
             optimizer._update(self.dense_flat, self.dense_grad_flat, None)
         self._end_of_step()
         return loss
+
+    def _update_tables(self, optimizer):
+        optimizer._update(self.emb, self.emb_grad, self.emb_touched)
 
     def train_on_batch_graph(self, ids, labels, optimizer: optimizers.Optimizer, denom: int = 0):
         """Same step as train_on_batch, replayed from a CUDA graph captured on first use (per batch size):
@@ -288,10 +295,10 @@ class DCN(torch.nn.Module):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self._run_step(b, B, denom)
-                self._sync_gradients()
                 optimizer.advance_device_hyper()
                 with torch.no_grad():
-                    optimizer._update(self.emb, self.emb_grad, self.emb_touched)
+                    self._update_tables(optimizer)
+                    self._sync_gradients()
                     optimizer._update(self.dense_flat, self.dense_grad_flat, None)
                 self._end_of_step()
             b[key] = g                         # capturing does not execute: host and device step counters unchanged
@@ -301,70 +308,6 @@ class DCN(torch.nn.Module):
         b[key].replay()
         optimizer.iterations += 1
         return b["loss"]
-
-    # ------------------------------------------------------------------ pipelined AdamW (single GPU)
-    def train_on_batch_pipelined(self, ids, labels, optimizer: optimizers.AdamW, next_ids, denom: int = 0):
-        """Same result as train_on_batch (bit for bit) with the table sweep taken off the critical path: only the rows the
-        NEXT batch gathers (`next_ids`, (B, F)) get this step's AdamW update on the main stream (krs_adamw_rows); every
-        other row is swept on a side stream under the next step's forward / backward (krs_adamw_skip).  The scatter of step
-        t+1 writes arena rows and a touched bitmap the cold sweep of step t never reads (double-buffered bitmaps; the rows
-        it scatters to are exactly the pre-updated ones the sweep skips).  Call finish_pipeline() before reading the
-        tables or switching back to train_on_batch."""
-        if not isinstance(optimizer, optimizers.AdamW) or getattr(optimizer, "_hyper_dev", None) is not None:
-            raise ValueError("train_on_batch_pipelined needs a host-stepped AdamW / Adam optimizer")
-        B = ids.shape[0]
-        b = self._step_buffers(B)
-        st = getattr(self, "_pipe", None)
-        if st is None:
-            st = self._pipe = dict(side=torch.cuda.Stream(device=self.device_), cold_done=None, cur=0,
-                                   touched=[self.emb_touched, torch.zeros_like(self.emb_touched)],
-                                   pre=torch.zeros_like(self.emb_touched),
-                                   row_off=(C.c_int64 * self.F)(*[int(o) for o in self.row_off]))
-        if "next_ids" not in b:
-            b["next_ids"] = torch.empty_like(b["ids"])
-        cur = st["cur"]
-        t_cur = st["touched"][cur]
-        for f in range(self.F):                              # this step's scatter marks rows in the current bitmap
-            b["plan"].arr[f].touched = t_cur[self.row_off[f] // 32:].data_ptr()
-        loss = self.forward_backward(ids, labels, denom)
-        self._sync_gradients()
-        optimizer.iterations += 1
-        main = torch.cuda.current_stream(self.device_)
-        if st["cold_done"] is not None:
-            main.wait_event(st["cold_done"])                 # step t-1's sweep has reached every row
-        slots = optimizer._slots(self.emb, ("m", "v"))
-        hyp = (optimizer.learning_rate, optimizer.beta_1, optimizer.beta_2, optimizer.epsilon, optimizer.weight_decay,
-               max(optimizer.iterations, 1))
-        with torch.no_grad():
-            optimizer._update(self.dense_flat, self.dense_grad_flat, None)
-            b["next_ids"].copy_(next_ids if next_ids.dtype == torch.int32 else next_ids.to(torch.int32), non_blocking=True)
-            check(lib.krs_adamw_rows(ptr(self.emb), ptr(slots["m"]), ptr(slots["v"]), ptr(self.emb_grad), ptr(t_cur), ptr(st["pre"]),
-                                     ptr(b["next_ids"]), st["row_off"], B, self.F, self.E, *hyp, stream()))
-            hot_done = torch.cuda.Event()
-            hot_done.record(main)
-            side = st["side"]
-            side.wait_event(hot_done)
-            with torch.cuda.stream(side):
-                check(lib.krs_adamw_skip(ptr(self.emb), ptr(slots["m"]), ptr(slots["v"]), ptr(self.emb_grad), ptr(t_cur),
-                                         ptr(getattr(self, "emb_ever", None)), ptr(st["pre"]), self.emb.numel(), self.E, *hyp, None,
-                                         side.cuda_stream))
-                st["cold_done"] = torch.cuda.Event()
-                st["cold_done"].record(side)
-        st["cur"] = cur ^ 1
-        self._end_of_step()
-        return loss
-
-    def finish_pipeline(self):
-        """Joins the side stream of train_on_batch_pipelined and restores the single touched bitmap of train_on_batch."""
-        st = getattr(self, "_pipe", None)
-        if st is None:
-            return
-        if st["cold_done"] is not None:
-            torch.cuda.current_stream(self.device_).wait_event(st["cold_done"])
-        for b in self._bufs.values():
-            for f in range(self.F):
-                b["plan"].arr[f].touched = self.emb_touched[self.row_off[f] // 32:].data_ptr()
-        st["cur"] = 0
 
     def _end_of_step(self):
         """Hook for cross-rank ordering at the end of a step (row-sharded model)."""
@@ -391,4 +334,5 @@ class _ArenaGather(torch.autograd.Function):
         grads = [m.emb_grad[m.row_off[f]:] for f in range(m.F)]
         touched = [m.emb_touched[m.row_off[f] // 32:] for f in range(m.F)]
         plan.backward(gout, grads, touched)
+        m.emb._krs_arena_dirty = True
         return None, None, None

@@ -113,24 +113,12 @@ class BruteForceRetrieval(Retrieval):
         lead = q.shape[:-1]
         q2 = q.reshape(-1, q.shape[-1])
         ids = None if self.candidate_ids is None else self.candidate_ids.detach().to(torch.int32)
-        top_scores, top_ids = ops.top_k_scores(q2, cand, ids, self.k, cand_lo=self._lo_plane(cand))
+        top_scores, top_ids = ops.top_k_scores(q2, cand, ids, self.k)
         top_scores = top_scores.reshape(*lead, self.k)
         top_ids = top_ids.reshape(*lead, self.k)
         if self.return_scores:
             return top_scores, top_ids
         return top_ids
-
-    def _lo_plane(self, cand: torch.Tensor):
-        """Low-order TF32 plane of the candidates for the tensor-pipe scorer (csrc/topk.cu), computed once per version of
-        the candidate tensor (keyed on storage pointer, shape and torch's in-place version counter)."""
-        nc, d = cand.shape
-        if d % 4 != 0 or d > 64 or nc * d < (1 << 20) or not cand.is_contiguous():
-            return None
-        key = (cand.data_ptr(), tuple(cand.shape), cand._version)
-        if getattr(self, "_lo_key", None) != key:
-            self._lo = ops.split_candidates_lo(cand)
-            self._lo_key = key
-        return self._lo
 
     def compute_output_shape(self, input_shape):
         s = tuple(input_shape[:-1]) + (self.k,)

@@ -159,6 +159,7 @@ class _GatherFn(torch.autograd.Function):
             grads, touched = [], []
             for t in plan.tables:
                 a, b = ensure_arena(t)
+                t._krs_arena_dirty = True
                 grads.append(a)
                 touched.append(b)
             plan.backward(gout, grads, touched)
@@ -354,17 +355,8 @@ def set_topk_engine(name: str) -> None:
     check(lib.krs_set_topk_engine({"auto": 0, "ffma": 1, "tcgen05": 2}[name]))
 
 
-def split_candidates_lo(cand: torch.Tensor) -> torch.Tensor:
-    """C_lo = tf32_rn(C - trunc_tf32(C)) for the tensor-pipe scorer (krs_topk_split_candidates)."""
-    cand = _c(cand)
-    lo = torch.empty_like(cand)
-    check(lib.krs_topk_split_candidates(ptr(cand), ptr(lo), cand.shape[0], cand.shape[1], stream()))
-    return lo
-
-
-def top_k_scores(q: torch.Tensor, cand: torch.Tensor, cand_ids: torch.Tensor | None, k: int, cand_lo: torch.Tensor | None = None):
-    """Streaming Q @ C^T + exact top-k (never materialises the score matrix).  `cand_lo` (optional): the precomputed
-    low-order plane of `cand` (split_candidates_lo); the tensor-pipe kernel then streams it by TMA."""
+def top_k_scores(q: torch.Tensor, cand: torch.Tensor, cand_ids: torch.Tensor | None, k: int):
+    """Streaming Q @ C^T + exact top-k (never materialises the score matrix)."""
     q = _c(q)
     cand = _c(cand)
     nq, d = q.shape
@@ -373,8 +365,8 @@ def top_k_scores(q: torch.Tensor, cand: torch.Tensor, cand_ids: torch.Tensor | N
     ws = torch.empty((max(ws_bytes, 16),), dtype=torch.uint8, device=q.device)
     top_s = torch.empty((nq, k), dtype=torch.float32, device=q.device)
     top_i = torch.empty((nq, k), dtype=torch.int32, device=q.device)
-    check(lib.krs_topk_lo(ptr(q), ptr(cand), ptr(cand_lo), ptr(cand_ids), ptr(top_s), ptr(top_i), nq, nc, d, k, ptr(ws),
-                          ws.numel(), stream()))
+    check(lib.krs_topk(ptr(q), ptr(cand), ptr(cand_ids), ptr(top_s), ptr(top_i), nq, nc, d, k, ptr(ws), ws.numel(),
+                       stream()))
     return top_s, top_i
 
 

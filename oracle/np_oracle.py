@@ -71,9 +71,27 @@ def activation_grad(name, z: np.ndarray, a: np.ndarray) -> np.ndarray:
 # --------------------------------------------------------------------------- embedding
 def embedding_lookup(table: np.ndarray, ids: np.ndarray) -> np.ndarray:
     """keras.layers.Embedding.call == ops.take(table, ids, axis=0) (examples/dcn.py:430-435;
-    embed_reduce.py:178).  Out-of-range ids are clamped (the product clamps too)."""
-    ids = np.clip(np.asarray(ids).astype(np.int64), 0, table.shape[0] - 1)
-    return table[ids]
+    embed_reduce.py:178).
+
+    Out-of-range ids follow the backend the north star names (KERAS_BACKEND=jax on CPU): keras' jax `take`
+    is `jnp.take(x, indices, axis=axis)` with the default mode, which jax documents as "fill": negative
+    indices count from the end (idx + n), indices still outside [0, n) return NaN for floating tables, and the
+    transpose (the gradient scatter-add) drops them.  keras and jax are third-party and unpinned
+    (pyproject.toml:29-32: keras >= 3.10, jax unpinned); the rule is restated from the published jnp.take
+    contract.  The product follows this oracle (gather.cu resolve_id), not the other way round."""
+    ids, valid = resolve_ids(ids, table.shape[0])
+    out = table[np.where(valid, ids, 0)]
+    if not valid.all():
+        out = out.copy()
+        out[~valid] = np.nan
+    return out
+
+
+def resolve_ids(ids, vocab: int):
+    """jnp.take(mode="fill") index rule: (ids wrapped once from the end, mask of ids that address a row)."""
+    ids = np.asarray(ids).astype(np.int64)
+    ids = np.where(ids < 0, ids + vocab, ids)
+    return ids, (ids >= 0) & (ids < vocab)
 
 
 def _divide_no_nan(x: np.ndarray, d: np.ndarray) -> np.ndarray:
@@ -157,7 +175,7 @@ def embedding_grad(ids: np.ndarray, weights: np.ndarray | None, vocab: int, gout
     if reduce is None:
         reduce = ids.ndim == 2
     B = ids.shape[0]
-    ids2 = np.clip(ids.reshape(B, -1).astype(np.int64), 0, vocab - 1)
+    ids2, valid = resolve_ids(ids.reshape(B, -1), vocab)       # invalid ids receive no gradient (jnp.take "fill")
     H = ids2.shape[1]
     if weights is None or ((not reduce) and combiner != "sum"):
         w = np.ones((B, H), dtype=gout.dtype)
@@ -172,7 +190,8 @@ def embedding_grad(ids: np.ndarray, weights: np.ndarray | None, vocab: int, gout
         scale = _divide_no_nan(np.ones_like(d), d)
     grad = np.zeros((vocab, gout.shape[1]), dtype=gout.dtype)
     for h in range(H):
-        np.add.at(grad, ids2[:, h], (w[:, h:h + 1] * scale) * gout)
+        ok = valid[:, h]
+        np.add.at(grad, ids2[ok, h], ((w[:, h:h + 1] * scale) * gout)[ok])
     return grad
 
 
@@ -425,7 +444,56 @@ def sgd_step(p, g, lr=0.01):
     return (p - F32(lr) * g).astype(F32)
 
 
+def lazy_adam_step(p, m, v, g, step: int, lr=0.001, b1=0.9, b2=0.999, eps=1e-7, rows=None):
+    """keras Adam applied only to the rows that received gradient (the per-row form of the reference's SparseCore
+    path: jax/config_conversion.py:259-268 maps keras Adam onto embedding_spec.AdamOptimizerSpec, whose update visits
+    the looked-up rows only).  `rows`: boolean mask of the looked-up rows (default: rows with a non-zero gradient);
+    all other rows keep p, m and v."""
+    rows = np.any(g != 0, axis=-1) if rows is None else np.asarray(rows, bool)
+    p2, m2, v2 = adamw_step(p[rows], m[rows], v[rows], g[rows], step, lr=lr, b1=b1, b2=b2, eps=eps, wd=0.0)
+    p, m, v = p.copy(), m.copy(), v.copy()
+    p[rows], m[rows], v[rows] = p2, m2, v2
+    return p, m, v
+
+
+def ftrl_step(p, accum, linear, g, lr=0.001, lr_power=-0.5, l1=0.0, l2=0.0, beta=0.0, rows=None):
+    """keras Ftrl.update_step (third-party keras/src/optimizers/ftrl.py, restated; l2_shrinkage = 0 is the only form
+    jax/config_conversion.py:269-285 accepts), applied to the looked-up rows (`rows` mask; default g != 0)."""
+    rows = np.any(g != 0, axis=-1) if rows is None else np.asarray(rows, bool)
+    pr, ar, lr_, gr = p[rows], accum[rows], linear[rows], g[rows]
+    l2r = F32(l2) + F32(beta) / (F32(2.0) * F32(lr))
+    na = ar + gr * gr
+    pa, pn = np.power(ar, F32(-lr_power)), np.power(na, F32(-lr_power))
+    lin = lr_ + (gr - (pn - pa) / F32(lr) * pr)
+    quad = pn / F32(lr) + F32(2.0) * l2r
+    lc = np.clip(lin, F32(-l1), F32(l1))
+    p, accum, linear = p.copy(), accum.copy(), linear.copy()
+    p[rows], accum[rows], linear[rows] = ((lc - lin) / quad).astype(F32), na.astype(F32), lin.astype(F32)
+    return p, accum, linear
+
+
 # --------------------------------------------------------------------------- MOD sharding (C5)
+def route_requests(ids: np.ndarray, vocab: Sequence[int], num_shards: int, owner_row_off):
+    """Request lists of one rank's (B, F) id matrix (csrc/exchange.cu route): for every owner o, in position order, the
+    pairs (arena row on o, position b*F+f) of the ids o owns; ids that address no row (embedding_lookup) are left out.
+    owner_row_off[o][f] = first arena row of table f on owner o.  MOD layout as mod_route."""
+    ids = np.asarray(ids).astype(np.int64)
+    B, F = ids.shape
+    rows = [[] for _ in range(num_shards)]
+    pos = [[] for _ in range(num_shards)]
+    for b in range(B):
+        for f in range(F):
+            i = int(ids[b, f])
+            if i < 0:
+                i += int(vocab[f])
+            if not 0 <= i < int(vocab[f]):
+                continue
+            o = i % num_shards
+            rows[o].append(int(owner_row_off[o][f]) + i // num_shards)
+            pos[o].append(b * F + f)
+    return [np.asarray(r, np.int32) for r in rows], [np.asarray(q, np.int32) for q in pos]
+
+
 def mod_route(ids: np.ndarray, num_shards: int):
     """Row-wise MOD sharding: row r lives on shard r % S at local row r // S
     (jax/embedding_utils.py:187-197; tensorflow/distributed_embedding.py:316-328)."""

@@ -175,34 +175,6 @@ def test_c2_full_size_gather_properties():
     assert pop == uniq
 
 
-def test_pipelined_adamw_step_is_bitwise_equal_to_the_sequential_step():
-    """train_on_batch_pipelined (hot rows first, cold sweep on a side stream under the next step) must leave exactly the
-    parameters and moments of train_on_batch after every step, including duplicate ids inside and across batches."""
-    import keras_rs_b200 as K
-    rng = np.random.default_rng(21)
-    vocab, E, B = [64, 40, 33, 500], 32, 256
-    m1, m2 = _mk(vocab, E, 2, None, (16,), seed=6), _mk(vocab, E, 2, None, (16,), seed=6)
-    o1, o2 = K.optimizers.AdamW(0.01), K.optimizers.AdamW(0.01)
-    batches = [(np.stack([rng.integers(0, v, size=B) for v in vocab], axis=1).astype(np.int32), rng.uniform(size=B).astype(np.float32))
-               for _ in range(7)]
-    for step in range(6):
-        ids, y = batches[step]
-        l1 = float(m1.train_on_batch(dev(ids), dev(y), o1))
-        l2 = float(m2.train_on_batch_pipelined(dev(ids), dev(y), o2, dev(batches[step + 1][0])))
-        assert l1 == l2, f"loss differs at step {step}"
-    m2.finish_pipeline()
-    torch.cuda.synchronize()
-    assert o1.iterations == o2.iterations == 6
-    assert torch.equal(m1.emb, m2.emb) and torch.equal(m1.dense_flat, m2.dense_flat)
-    for slot in ("m", "v"):
-        assert torch.equal(o1._state[id(m1.emb)][slot], o2._state[id(m2.emb)][slot])
-    assert int(m2.emb_touched.abs().max()) == 0 and float(m2.emb_grad.abs().max()) == 0.0
-    # and the model keeps training correctly through the ordinary step afterwards
-    ids, y = batches[6]
-    assert float(m1.train_on_batch(dev(ids), dev(y), o1)) == float(m2.train_on_batch(dev(ids), dev(y), o2))
-    assert torch.equal(m1.emb, m2.emb)
-
-
 @pytest.mark.parametrize("opt_name", ["adamw", "adagrad"])
 def test_cuda_graph_step_matches_eager_step(opt_name):
     """train_on_batch_graph (one CUDA-graph replay per step, device-resident Adam step/alpha) must produce the

@@ -178,3 +178,15 @@ def test_mod_route_roundtrip():
     owner, local = O.mod_route(ids, 8)
     for i, o, l in zip(ids, owner, local):
         np.testing.assert_array_equal(sh[o][l], t[i])
+
+
+def test_embedding_lookup_out_of_range_ids_jnp_take_fill():
+    """jnp.take default mode "fill" (keras.ops.take on the JAX backend): negative ids wrap once, the rest is NaN forward
+    and dropped backward."""
+    tab = np.arange(12, dtype=np.float32).reshape(4, 3)
+    out = O.embedding_lookup(tab, np.array([0, -1, -4, -5, 4, 3]))
+    np.testing.assert_array_equal(out[[0, 1, 2, 5]], tab[[0, 3, 0, 3]])
+    assert np.isnan(out[[3, 4]]).all()
+    g = np.ones((6, 3), np.float32)
+    grad = O.embedding_grad(np.array([0, -1, -4, -5, 4, 3]), None, 4, g)
+    np.testing.assert_array_equal(grad[:, 0], [2, 0, 0, 2])
