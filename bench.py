@@ -4,7 +4,7 @@
 Dense 192-192-1, MSE, AdamW — the examples/dcn.py wiring) on N B200s, plus the fused embedding-gather
 HBM roofline and the CPU baseline.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c5|c3]
   torchrun: python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
 One step = gather -> 3x FeatureCross -> MLP -> MSE -> full backward -> embedding scatter-add ->
@@ -13,6 +13,22 @@ visited).  `value` times K steps with the batch already in HBM; `e2e` times the 
 through the public API from PINNED HOST buffers (H2D of ids+labels and a D2H read of the loss inside
 the timed region).  Inputs are far larger than L2 (3.3 GB of tables, random rows), so no flush is
 needed between iterations ("l2": "inputs_larger_than_L2").
+
+N > 1: tables are MOD row-sharded over the ranks (keras_rs_b200/sharded.py), dense layers data
+parallel, 65536 examples per GPU.  Before anything is timed every rank runs a PARITY SELF-CHECK of
+the row-sharded step (3 steps of a small shadow config against oracle/np_oracle.py on the global
+batch: per-step loss, every table shard, every dense weight); the JSON line carries
+`parity_check` and the process exits non-zero when it fails.  Weak scaling means constant work per
+GPU, so by default the vocabulary grows with N (`rows per shard` = the 1-GPU table: vocab x N per
+feature); `--fixed-global-vocab` keeps the stated 1e6-row tables and shards them (each GPU's AdamW
+sweep then shrinks by 1/N — reported as `c2_fixed_vocab` in the default run as well).
+
+--workload c5: BASELINE configs[4] at its stated size on 8 GPUs — 26 tables totalling 1e9 rows,
+embed_dim 128, global batch 524288, 3 low-rank (P=512) cross layers, Adagrad on the owner (64 GB of
+table + 64 GB of accumulator per GPU; no table-sized gradient exists).  With fewer GPUs the row
+count scales down with N (1.25e8 rows per GPU) and the workload string says so.
+--workload c3: BASELINE configs[2], the DLRM DotInteraction model (13 dense + 26 sparse features,
+embed_dim 128, batch 65536, examples/ml_perf wiring), 1 GPU, Adagrad.
 """
 from __future__ import annotations
 
@@ -34,26 +50,57 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--optimizer", default="adamw", choices=["adamw", "adagrad", "sgd"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c5", "c3"])
+    ap.add_argument("--optimizer", default=None, choices=["adamw", "adagrad", "sgd"])
     ap.add_argument("--engine", default="auto", choices=["auto", "ffma", "tcgen05", "tcgen05_ts"])
-    ap.add_argument("--batch", type=int, default=65536)
+    ap.add_argument("--batch", type=int, default=65536, help="examples per GPU")
     ap.add_argument("--features", type=int, default=26)
-    ap.add_argument("--vocab", type=int, default=1_000_000)
-    ap.add_argument("--embed-dim", type=int, default=32)
+    ap.add_argument("--vocab", type=int, default=None, help="rows per table (c2: 1e6; c5: 1e9/26)")
+    ap.add_argument("--embed-dim", type=int, default=None)
     ap.add_argument("--cross-layers", type=int, default=3)
     ap.add_argument("--cpu-steps", type=int, default=1)
     ap.add_argument("--cpu-budget-s", type=float, default=150.0, help="wall-time bound of the CPU legs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gather-variant", type=int, default=0)
     ap.add_argument("--graph", action="store_true", help="replay the step from a CUDA graph (1 GPU; the eager step already has no launch gaps)")
-    ap.add_argument("--projection-dim", type=int, default=0, help="low-rank FeatureCross (ml_perf uses 512); 0 = full rank")
+    ap.add_argument("--projection-dim", type=int, default=None, help="low-rank FeatureCross (ml_perf uses 512); 0 = full rank")
     ap.add_argument("--dense-units", default="192,192")
-    return ap.parse_args()
+    ap.add_argument("--fixed-global-vocab", action="store_true",
+                    help="N > 1: keep the stated table size and shard it (per-GPU optimizer work shrinks with N)")
+    ap.add_argument("--skip-parity", action="store_true", help="N > 1: skip the parity self-check (never for reported numbers)")
+    ap.add_argument("--no-fixed-vocab-leg", action="store_true", help="N > 1, c2: skip the extra `c2_fixed_vocab` measurement")
+    a = ap.parse_args()
+    if a.workload == "c5":
+        a.optimizer = a.optimizer or "adagrad"
+        a.embed_dim = a.embed_dim or 128
+        a.projection_dim = 512 if a.projection_dim is None else a.projection_dim
+    elif a.workload == "c3":
+        a.optimizer = a.optimizer or "adagrad"
+        a.embed_dim = a.embed_dim or 128
+        a.vocab = a.vocab or 1_000_000
+    a.optimizer = a.optimizer or "adamw"
+    a.embed_dim = a.embed_dim or 32
+    a.projection_dim = a.projection_dim or 0
+    return a
 
 
-def workload_name(a):
+def c5_vocab(world):
+    """26 tables totalling 1e9 rows on 8 GPUs; 1.25e8 rows per GPU when run on fewer."""
+    total = 1_000_000_000 if world >= 8 else 125_000_000 * world
+    return -(-total // 26)
+
+
+def workload_name(a, world=1, vocab=None):
+    vocab = vocab or a.vocab or 1_000_000
     rank_s = f"low-rank P={a.projection_dim}" if a.projection_dim else "full-rank"
-    return (f"DCN-v2 C2: {a.features} categorical features, vocab {a.vocab} each, embed_dim={a.embed_dim}, "
+    if a.workload == "c5":
+        return (f"DCN-v2 C5: {a.features} row-sharded tables totalling {vocab * a.features:.3e} rows, embed_dim={a.embed_dim}, "
+                f"global batch={a.batch * world}, {a.cross_layers} {rank_s} cross layers, Dense {a.dense_units.replace(',', '-')}-1, MSE, "
+                f"{a.optimizer}, {world} GPUs")
+    if a.workload == "c3":
+        return (f"DLRM C3: 13 dense + {a.features} sparse features, vocab {vocab} each, embed_dim={a.embed_dim}, batch={a.batch}, "
+                f"DotInteraction, bottom 512-256-{a.embed_dim}, top 1024-1024-512-256-1, BCE, {a.optimizer}")
+    return (f"DCN-v2 C2: {a.features} categorical features, vocab {vocab} each, embed_dim={a.embed_dim}, "
             f"batch={a.batch}, {a.cross_layers} {rank_s} cross layers, Dense {a.dense_units.replace(',', '-')}-1, MSE, "
             f"{a.optimizer}")
 
@@ -62,26 +109,24 @@ def workload_name(a):
 def run_reference(a):
     """The reference's own CPU path for this workload.  keras/jax cannot be installed here,
     so this times the oracle PORT (oracle/torch_ref.py: the Keras op sequence one-for-one in torch-CPU),
-    all host threads, each step one full batch of the same workload."""
+    all host threads: exactly --warmup untimed and --steps timed steps, each a bounded sample of the workload
+    when full-size steps would not fit the budget (oracle/torch_ref.py time_reference_arm)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import torch_ref as T
     cores = T.usable_cores()        # min(cpu_count, affinity, cgroup quota): the threads the host really grants
-    # a full step of this workload costs ~50 s of CPU time (the dense AdamW sweep over 3.3 GB of tables dominates),
-    # so the run is bounded: 1 warm-up step, then timed steps until --cpu-budget-s is spent
-    r = T.time_cpu_baseline(B=a.batch, F=a.features, V=a.vocab, E=a.embed_dim, L=a.cross_layers, steps=a.steps,
-                            warmup=min(a.warmup, 1), optimizer=a.optimizer, threads=cores, budget_s=a.cpu_budget_s)
+    units = tuple(int(u) for u in a.dense_units.split(",") if u)
+    r = T.time_reference_arm(B=a.batch, F=a.features, V=a.vocab or 1_000_000, E=a.embed_dim, L=a.cross_layers, units=units,
+                             steps=a.steps, warmup=a.warmup, optimizer=a.optimizer, threads=cores, budget_s=max(a.cpu_budget_s, 240.0))
     line = {
         "impl": "reference", "metric": "examples/sec", "value": r["value"], "unit": "examples/s", "n_gpus": a.gpus,
-        "steps": r["steps"], "warmup": r["warmup"], "requested_steps": a.steps, "requested_warmup": a.warmup,
-        "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a), "global_batch": a.batch},
         "cpu_baseline": {"value": r["value"], "unit": "examples/s", "cores": cores, "kind": "port",
-                         "sample": f"{r['steps']} timed full step(s) of batch {a.batch} after {r['warmup']} warm-up, bounded to "
-                                   f"{a.cpu_budget_s:.0f} s (torch-CPU restatement of the Keras op sequence on all host "
-                                   "cores; keras/jax not installable)"},
+                         "sample": r["sample"] + " (torch-CPU restatement of the Keras op sequence on all host cores; "
+                                                 "keras/jax not installable)"},
         "e2e": {"value": r["value"], "unit": "examples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -127,6 +172,63 @@ class Clocks:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# --------------------------------------------------------------------------------------- parity self-check (N > 1)
+def sharded_parity_check(world, rank, optimizer, engine):
+    """3 steps of a small shadow config through the real multi-process ShardedDCN vs np_oracle on the global batch.
+    Runs twice: on the exact-fp32 engine (isolates the exchange: loss 1e-5, parameters 1e-5 / AdamW 5e-5 because
+    1/(sqrt(v)+eps) amplifies rounding of tiny gradients) and on the benchmark's engine (loss at 1e-5)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import keras_rs_b200 as K
+    from keras_rs_b200.sharded import ShardedDCN
+    from oracle import np_oracle as O
+    from oracle import parity as PAR
+
+    npy = lambda t: t.detach().float().cpu().numpy()
+    vocab, E, Bl, steps = [1000, 777, 1000, 50], 32, 256, 3
+    out = {"world": world, "steps": steps, "config": f"{len(vocab)} tables {vocab} rows, E={E}, {Bl} examples per rank, 2 cross layers, {optimizer}"}
+    ok = True
+    for eng in (["ffma", engine] if engine != "ffma" else ["ffma"]):
+        K.set_gemm_engine(eng)
+        m = ShardedDCN(vocab, rank=rank, world=world, embedding_dim=E, num_cross_layers=2, dense_units=(32,), seed=11)
+        shards = [None] * world
+        dist.all_gather_object(shards, [npy(t) for t in m.tables()])
+        tables = [O.mod_unshard_table([shards[s][f] for s in range(world)]) for f in range(len(vocab))]
+        tr = PAR.OracleTrainer(PAR.params_of(tables, m.cross, m.mlp), optimizer, lr=0.01)
+        opt = {"adamw": K.optimizers.AdamW, "adagrad": K.optimizers.Adagrad, "sgd": K.optimizers.SGD}[optimizer](0.01)
+        rel_loss = 0.0
+        for gids, gy in PAR.make_batches(vocab, Bl, world, steps, seed=4242, bad_ids=True):
+            ref = tr.train(gids, gy)
+            loss = m.train_on_batch(torch.from_numpy(gids[rank * Bl:(rank + 1) * Bl]).cuda(),
+                                    torch.from_numpy(gy[rank * Bl:(rank + 1) * Bl]).cuda(), opt, denom=Bl * world)
+            tot = loss.clone()
+            dist.all_reduce(tot)
+            rel_loss = max(rel_loss, abs(float(tot) - ref) / max(abs(ref), 1e-6))
+        m.check_exchange_errors()
+        rel_p = 0.0
+        for f, t in enumerate(m.tables()):
+            rel_p = max(rel_p, PAR.max_rel(npy(t), tr.P["tables"][f][rank::world]))
+        for c, pc in zip(m.cross, tr.P["cross"]):
+            rel_p = max(rel_p, PAR.max_rel(npy(c.kernel), pc["V"]))
+        for d, (W, b, _) in zip(m.mlp, tr.P["mlp"]):
+            rel_p = max(rel_p, PAR.max_rel(npy(d.kernel), W))
+        t = torch.tensor([rel_loss, rel_p], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        rel_loss, rel_p = float(t[0]), float(t[1])
+        tol_p = 5e-5 if optimizer == "adamw" else 1e-5
+        if eng == "ffma":
+            out.update(max_rel_loss=rel_loss, max_rel_params=rel_p, tol_loss=1e-5, tol_params=tol_p)
+            ok = ok and rel_loss <= 1e-5 and rel_p <= tol_p
+        else:
+            out.update({"max_rel_loss_" + eng: rel_loss, "max_rel_params_" + eng: rel_p})
+            ok = ok and rel_loss <= 1e-5
+        m.close()
+        del m
+    out["ok"] = bool(ok)
+    return out
+
+
 # --------------------------------------------------------------------------------------- our arm
 def run_ours(a):
     import torch
@@ -145,9 +247,28 @@ def run_ours(a):
     engine = a.engine
     if engine == "auto":
         engine = os.environ.get("KRS_GEMM_ENGINE", "tcgen05_ts")   # tensor-pipe 3xTF32 (fp32-level accuracy); "ffma" = exact fp32 FMA
+
+    if a.workload == "c3":
+        return run_c3(a, engine)
+
+    parity = None
+    if world > 1 and not a.skip_parity:
+        parity = sharded_parity_check(world, rank, a.optimizer, engine)
+        if not parity["ok"]:
+            if rank == 0:
+                print(json.dumps({"metric": "examples/sec", "value": None, "n_gpus": world, "parity_check": parity,
+                                  "error": "row-sharded step disagrees with the oracle; nothing was timed"}), flush=True)
+            dist.destroy_process_group()
+            sys.exit(1)
     K.set_gemm_engine(engine)
 
-    B, F, V, E, L = a.batch, a.features, a.vocab, a.embed_dim, a.cross_layers
+    B, F, E, L = a.batch, a.features, a.embed_dim, a.cross_layers
+    if a.workload == "c5":
+        V = a.vocab or c5_vocab(world)
+    else:
+        V = a.vocab or 1_000_000
+        if world > 1 and not a.fixed_global_vocab:
+            V = V * world                         # constant rows per shard: weak scaling with constant per-GPU work
     units = tuple(int(u) for u in a.dense_units.split(",") if u)
     proj = a.projection_dim or None
     peaks = {}
@@ -158,22 +279,30 @@ def run_ours(a):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
 
-    if world > 1:
-        from keras_rs_b200.sharded import ShardedDCN
-        model = ShardedDCN([V] * F, embedding_dim=E, num_cross_layers=L, dense_units=units, projection_dim=proj,
-                           seed=1234, rank=rank, world=world)
-    else:
-        model = DCN([V] * F, embedding_dim=E, num_cross_layers=L, dense_units=units, projection_dim=proj, seed=1234)
-    opt = {"adamw": lambda: K.optimizers.AdamW(0.01), "adagrad": lambda: K.optimizers.Adagrad(0.01),
-           "sgd": lambda: K.optimizers.SGD(0.01)}[a.optimizer]()
+    def make_model(vocab):
+        if world > 1 or a.workload == "c5":
+            from keras_rs_b200.sharded import ShardedDCN
+            return ShardedDCN([vocab] * F, embedding_dim=E, num_cross_layers=L, dense_units=units, projection_dim=proj,
+                              seed=1234, rank=rank, world=world)
+        return DCN([vocab] * F, embedding_dim=E, num_cross_layers=L, dense_units=units, projection_dim=proj, seed=1234)
+
+    def make_opt():
+        return {"adamw": lambda: K.optimizers.AdamW(0.01), "adagrad": lambda: K.optimizers.Adagrad(0.01),
+                "sgd": lambda: K.optimizers.SGD(0.01)}[a.optimizer]()
+
+    model, opt = make_model(V), make_opt()
+    sharded = hasattr(model, "cg")
 
     # synthetic Criteo-shaped data: NB distinct batches, pinned on the host and resident on the device
     NB = 4
     g = torch.Generator().manual_seed(1234 + rank)
-    host_ids = [torch.randint(0, V, (B, F), generator=g, dtype=torch.int32).pin_memory() for _ in range(NB)]
-    host_y = [torch.rand((B,), generator=g).pin_memory() for _ in range(NB)]
-    dev_ids = [t.cuda() for t in host_ids]
-    dev_y = [t.cuda() for t in host_y]
+
+    def make_data(vocab):
+        hi = [torch.randint(0, vocab, (B, F), generator=g, dtype=torch.int32).pin_memory() for _ in range(NB)]
+        hy = [torch.rand((B,), generator=g).pin_memory() for _ in range(NB)]
+        return hi, hy, [t.cuda() for t in hi], [t.cuda() for t in hy]
+
+    host_ids, host_y, dev_ids, dev_y = make_data(V)
     denom = B * world
 
     def barrier():
@@ -199,9 +328,9 @@ def run_ours(a):
         return ms
 
     # ---- device-resident steps ("value") --------------------------------------------------
-    use_graph = a.graph and world == 1
+    use_graph = a.graph and not sharded
     if use_graph:
-        try:                                           # capture once (also validates NCCL capture on N > 1)
+        try:
             model.train_on_batch_graph(dev_ids[0], dev_y[0], opt, denom)
             torch.cuda.synchronize()
         except Exception as exc:                       # pragma: no cover
@@ -222,6 +351,8 @@ def run_ours(a):
     clk = clocks.stop() if rank == 0 else None
     ms_step = ms_total / a.steps
     value = B * world / (ms_step * 1e-3)
+    if sharded:
+        model.check_exchange_errors()
 
     # ---- end-to-end through the public API from pinned host buffers ("e2e") ----------------
     loss_host = torch.zeros((a.steps + a.warmup + 1,), dtype=torch.float32).pin_memory()
@@ -235,19 +366,20 @@ def run_ours(a):
     h2d = host_ids[0].numel() * 4 + host_y[0].numel() * 4
     final_loss = float(loss_host[(a.steps + 2) % loss_host.numel()])
 
+    # ---- phase breakdown of the row-sharded step (CUDA events on every rank, max over ranks) ----------------
+    phases = None
+    if sharded:
+        phases = sharded_phases(model, opt, dev_ids, dev_y, B, denom, world, dist if world > 1 else None)
+
     # ---- per-kernel measurements (rank 0 GPU, device resident, CUDA events on the launch stream) ----
     kern = {}
-    base = model.local if hasattr(model, "local") else model
-    if world == 1:
+    base = model
+    if not sharded:
         bufs = base._step_buffers(B)
-        plan = bufs["plan"]
         out = bufs["xs"][0]
         s = stream()
         # distinct id batches per launch so rows are re-fetched from HBM
-        plans = []
-        for i in range(NB):
-            p = K.ops.GatherPlan(base._feature_list(dev_ids[i]))
-            plans.append(p)
+        plans = [K.ops.GatherPlan(base._feature_list(dev_ids[i])) for i in range(NB)]
 
         def gather_i(i):
             p = plans[i % NB]
@@ -265,7 +397,7 @@ def run_ours(a):
             check(lib.krs_cross_fwd(ptr(x0), ptr(x0), ptr(c0.down_proj_kernel), ptr(c0.kernel), ptr(c0.bias), 0.0, 0, ptr(x1),
                                     ptr(h2), None, ptr(hp0), B, base.D, proj or 0, s))
 
-        ms_c = timed(cross_i, 5, 2) / 5
+        ms_c = timed(cross_i, 5, 3) / 5
         flops = 4.0 * B * base.D * proj if proj else 2.0 * B * base.D * base.D
         kern["cross_fwd"] = {"ms": ms_c, "TFLOPs": flops / ms_c * 1e-9, "flops": flops, "engine": engine}
 
@@ -273,12 +405,12 @@ def run_ours(a):
             opt._update(base.emb, base.emb_grad, base.emb_touched)
 
         if a.optimizer == "adamw":     # dense-exact sweep: p, m, v read + written, g read + re-zeroed
-            ms_a = timed(adamw_i, 5, 2) / 5
+            ms_a = timed(adamw_i, 5, 3) / 5
             # rows that ever received a gradient move 24 B per parameter (p, m, v read + written), the others 8 B (p only)
             ever = getattr(base, "emb_ever", None)
             hot = 1.0 if ever is None else float(torch.tensor([bin(int(x) & 0xFFFFFFFF).count("1") for x in ever[:65536].tolist()]).sum()) / (65536 * 32.0)
             adam_bytes = int(base.emb.numel() * 4 * (6 * hot + 2 * (1.0 - hot)))
-            kern["adamw_tables"] = {"ms": ms_a, "GBps": adam_bytes / ms_a * 1e-6, "bytes": adam_bytes}
+            kern["adamw_tables"] = {"ms": ms_a, "GBps": adam_bytes / ms_a * 1e-6, "bytes": adam_bytes, "ever_touched_fraction": hot}
 
         def scatter_i(i):
             p = plans[i % NB]
@@ -287,16 +419,16 @@ def run_ours(a):
                 p.arr[f].touched = base.emb_touched[base.row_off[f] // 32:].data_ptr()
             check(lib.krs_gather_bwd(p.arr, p.F, B, ptr(bufs["ga"]), base.D, s))
 
-        ms_s = timed(scatter_i, 5, 2) / 5
+        ms_s = timed(scatter_i, 5, 3) / 5
         kern["gather_bwd"] = {"ms": ms_s, "GBps": (B * F * E * 4 * 3 + B * F * 4) / ms_s * 1e-6}
         base.emb_grad.zero_(); base.emb_touched.zero_()
 
     # ---- in-situ per-call profile of the eager step (CUDA events around every C-ABI call) -------------------
     step_profile = None
-    if world == 1:
+    if not sharded:
         import collections
         names = ["krs_gather_fwd", "krs_cross_fwd", "krs_dense_fwd", "krs_loss_fwd_bwd", "krs_dense_bwd", "krs_cross_bwd",
-                 "krs_gather_bwd", "krs_adamw", "krs_sgd_adagrad", "krs_adam_hyper_advance"]
+                 "krs_gather_bwd", "krs_adamw", "krs_adamw_cold", "krs_sgd_adagrad", "krs_adam_hyper_advance"]
         recs = []
         orig = {n: getattr(lib, n) for n in names}
 
@@ -314,7 +446,7 @@ def run_ours(a):
             setattr(lib, n, wrap(n, orig[n]))
         try:
             t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            for i in range(2):
+            for i in range(3):
                 base.train_on_batch(dev_ids[i % NB], dev_y[i % NB], opt, denom)
             recs.clear()
             t0.record()
@@ -332,6 +464,24 @@ def run_ours(a):
             for n in names:
                 setattr(lib, n, orig[n])
 
+    # ---- N > 1, c2: the stated 1e6-row tables sharded over the ranks (per-GPU optimizer sweep shrinks with N) ----
+    fixed_leg = None
+    if world > 1 and a.workload == "c2" and not a.fixed_global_vocab and not a.no_fixed_vocab_leg:
+        model.close()
+        del model, opt, host_ids, host_y, dev_ids, dev_y
+        torch.cuda.empty_cache()
+        V2 = a.vocab or 1_000_000
+        model, opt = make_model(V2), make_opt()
+        host_ids, host_y, dev_ids, dev_y = make_data(V2)
+        k2 = max(min(a.steps, 10), 3)
+        m2, o2, di2, dy2 = model, opt, dev_ids, dev_y
+        ms2 = timed(lambda i: m2.train_on_batch(di2[i % NB], dy2[i % NB], o2, denom), k2, 3) / k2
+        model.check_exchange_errors()
+        fixed_leg = {"workload": workload_name(a, world, V2) + f", tables sharded over {world} GPUs", "ms_per_step": ms2,
+                     "value": B * world / (ms2 * 1e-3), "steps": k2, "warmup": 3}
+
+    if sharded:
+        model.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -339,7 +489,7 @@ def run_ours(a):
 
     # ---- CPU baseline on the host cores (bounded sample; rank 0, N=1 only) --------------------------
     cpu = None
-    if world == 1 and not a.no_cpu_baseline:
+    if world == 1 and not a.no_cpu_baseline and a.workload == "c2":
         del model
         torch.cuda.empty_cache()
         from oracle import torch_ref as T
@@ -351,7 +501,11 @@ def run_ours(a):
                          "here)", "ms_per_step": r["ms_per_step"]}
 
     n_mlp = len(units) + 1
-    launches_per_step = 1 + L * (2 if proj else 1) + n_mlp + 1 + 3 * n_mlp + L * (5 if proj else 3) + 1 + 2
+    dense_launches = L * (2 if proj else 1) + n_mlp + 1 + 3 * n_mlp + L * (5 if proj else 3)
+    if sharded:   # route (count, scan, fill) + 3 barriers + gather_push + slot scan (2) + grad_pull + table update (+ fold) + dense update
+        launches_per_step = 3 + 3 * (world > 1) + 1 + dense_launches + 2 + 1 + (2 if a.optimizer == "adamw" else 1) + 1
+    else:
+        launches_per_step = 1 + dense_launches + 1 + 2 + (1 if a.optimizer == "adamw" else 0)
     # ncu-measured DRAM traffic per launch of the two kernels below (profiles/ncu_traffic.json, written from the
     # committed `ncu --set full` captures by profiles/summarize.py; null when no capture of that kernel is committed)
     traffic = {}
@@ -381,13 +535,18 @@ def run_ours(a):
                 if "bf16_tflops" in peaks else "fallback 1590 TF/s bf16 / 6",
                 "algorithmic_flops": ck["flops"], "ms": ck["ms"], "engine": engine,
                 "traffic": (traffic.get("gemm_tc_kernel") or {}).get("dram_bytes")}
+    par = f"dp{world}"
+    if sharded:
+        par += ("+mod-row-sharded tables, routed exchange over NVLink peer memory (krs_xchg_*), owner-side fused optimizer; "
+                + ("rows per shard constant in N (vocab x N)" if (a.workload == "c2" and not a.fixed_global_vocab) else
+                   "stated global table size sharded over the ranks"))
     line = {
         "metric": "examples/sec", "value": value, "unit": "examples/s", "n_gpus": world, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a), "global_batch": B * world, "parallelism": f"dp{world}" + (
-            "+mod-row-sharded tables over NVLink peer memory" if world > 1 else ""), "gemm_engine": engine,
-            "l2": "inputs_larger_than_L2", "final_loss": final_loss, "launch": "cuda_graph" if use_graph else "eager"},
+        "config": {"workload": workload_name(a, world, V), "global_batch": B * world, "parallelism": par, "gemm_engine": engine,
+                   "l2": "inputs_larger_than_L2", "final_loss": final_loss, "launch": "cuda_graph" if use_graph else "eager",
+                   "rows_per_gpu": int(model_rows(V, F, world))},
         "clocks": clk,
         "e2e": {"value": e2e_value, "unit": "examples/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4},
@@ -396,9 +555,149 @@ def run_ours(a):
         "gpu_launches": launches_per_step * a.steps + split_launches,
         "roofline": roof, "roofline_gather": roof_gather, "kernels": kern, "step_profile_ms": step_profile, "cpu_baseline": cpu,
     }
+    if parity is not None:
+        line["parity_check"] = parity
+    if phases is not None:
+        line["phases_ms"] = phases
+    if fixed_leg is not None:
+        line["c2_fixed_vocab"] = fixed_leg
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def model_rows(V, F, world):
+    return -(-V // world) * F
+
+
+def sharded_phases(model, opt, dev_ids, dev_y, B, denom, world, dist):
+    """Per-phase device time of the row-sharded step (CUDA events; max over ranks).  The phases are separated by the
+    protocol's own barriers, so the sum is slightly above the step time of the timed loop (no overlap of the dense
+    all-reduce here)."""
+    import torch
+    from keras_rs_b200._lib import stream
+    s = stream()
+    b = model._step_buffers(B)
+    acc = {}
+    reps = 5
+
+    def ev():
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    for it in range(reps + 1):
+        b["ids"].copy_(dev_ids[it % len(dev_ids)])
+        b["labels"].copy_(dev_y[it % len(dev_y)])
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e = [ev()]
+        model._route(b, B, s); e.append(ev())
+        model._barrier(b, s); e.append(ev())
+        model._serve(b, s, True); e.append(ev())
+        model._barrier(b, s); e.append(ev())
+        cur = model._dense_step(b, B, denom, s); e.append(ev())
+        if dist is not None:
+            dist.all_reduce(model.dense_grad_flat)
+        e.append(ev())
+        model._barrier(b, s); e.append(ev())
+        model._pull_grads(b, s); e.append(ev())
+        model._parity ^= 1
+        opt.iterations += 1
+        with torch.no_grad():
+            model._update_tables(opt); e.append(ev())
+            opt._update(model.dense_flat, model.dense_grad_flat, None); e.append(ev())
+        torch.cuda.synchronize()
+        if it == 0:
+            continue
+        names = ["route", "barrier_1", "owner_gather_push", "barrier_2", "dense_fwd_bwd", "dense_allreduce", "barrier_3",
+                 "slot_scan+grad_pull", "table_optimizer", "dense_optimizer"]
+        for n, x, y in zip(names, e[:-1], e[1:]):
+            acc[n] = acc.get(n, 0.0) + x.elapsed_time(y) / reps
+    keys = list(acc)
+    t = torch.tensor([acc[k] for k in keys], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    out = {k: round(float(v), 4) for k, v in zip(keys, t)}
+    P = B * model.F
+    row_bytes = model.E * 4
+    remote = (world - 1) / world
+    out["nvlink_GBps_gather_push"] = round(P * row_bytes * remote / max(out["owner_gather_push"], 1e-9) * 1e-6, 1)
+    out["nvlink_GBps_grad_pull"] = round(P * row_bytes * remote / max(out["slot_scan+grad_pull"], 1e-9) * 1e-6, 1)
+    out["sum"] = round(sum(acc.values()), 4)
+    return out
+
+
+# --------------------------------------------------------------------------------------- C3 (DLRM) on one GPU
+def run_c3(a, engine):
+    import torch
+    import keras_rs_b200 as K
+    from keras_rs_b200.dlrm import DLRM
+
+    K.set_gemm_engine(engine)
+    B, F, V, E = a.batch, a.features, a.vocab, a.embed_dim
+    model = DLRM([V] * F, embedding_dim=E, num_dense=13, bottom_mlp_dims=(512, 256, E), interaction="dot", seed=1234)
+    opt = {"adamw": lambda: K.optimizers.AdamW(0.01), "adagrad": lambda: K.optimizers.Adagrad(0.01),
+           "sgd": lambda: K.optimizers.SGD(0.01)}[a.optimizer]()
+    NB = 4
+    g = torch.Generator().manual_seed(1234)
+    h_ids = [torch.randint(0, V, (B, F), generator=g, dtype=torch.int32).pin_memory() for _ in range(NB)]
+    h_dense = [torch.rand((B, 13), generator=g).pin_memory() for _ in range(NB)]
+    h_y = [torch.randint(0, 2, (B,), generator=g).float().pin_memory() for _ in range(NB)]
+    d_ids, d_dense, d_y = [t.cuda() for t in h_ids], [t.cuda() for t in h_dense], [t.cuda() for t in h_y]
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    clocks = Clocks(int(os.environ.get("LOCAL_RANK", "0")))
+    clocks.start()
+    ms_step = timed(lambda i: model.train_on_batch(d_dense[i % NB], d_ids[i % NB], d_y[i % NB], opt), a.steps, a.warmup) / a.steps
+    clk = clocks.stop()
+    loss_host = torch.zeros((1,), dtype=torch.float32).pin_memory()
+
+    def e2e(i):
+        j = i % NB
+        loss = model.train_on_batch(h_dense[j].cuda(non_blocking=True), h_ids[j].cuda(non_blocking=True), h_y[j].cuda(non_blocking=True), opt)
+        loss_host.copy_(loss.reshape(1), non_blocking=True)
+
+    ms_e2e = timed(e2e, a.steps, 3) / a.steps
+    # DotInteraction kernels alone (the C3 hot op): HBM roofline
+    feats = [torch.randn((B, E), device="cuda") for _ in range(F + 1)]
+    dot = K.layers.DotInteraction()
+    ms_fwd = timed(lambda i: dot(feats), 10, 3) / 10
+    n = F + 1
+    out_dim = n * (n - 1) // 2
+    fwd_bytes = B * n * E * 4 + B * out_dim * 4
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    line = {
+        "metric": "examples/sec", "value": B / (ms_step * 1e-3), "unit": "examples/s", "n_gpus": 1, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "global_batch": B, "gemm_engine": engine, "l2": "inputs_larger_than_L2",
+                   "launch": "eager (public layers through autograd Functions over the C ABI)"},
+        "clocks": clk,
+        "e2e": {"value": B / (ms_e2e * 1e-3), "unit": "examples/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": B * F * 4 + B * 13 * 4 + B * 4, "d2h_bytes_per_step": 4},
+        "roofline": {"kernel": "dot_fwd kernel (DotInteraction forward, 27 features x 128)", "bound": "hbm",
+                     "achieved": fwd_bytes / ms_fwd * 1e-6, "peak": hbm_peak, "unit": "GB/s", "frac": fwd_bytes / ms_fwd * 1e-6 / hbm_peak,
+                     "algorithmic_bytes": fwd_bytes, "ms": ms_fwd, "traffic": None},
+        "cpu_baseline": None,
+    }
+    print(json.dumps(line), flush=True)
 
 
 def main():

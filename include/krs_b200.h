@@ -278,10 +278,11 @@ int krs_rows_apply(float* p, float* s1, float* s2, float* compact, const int32_t
                    int64_t cap_rows, int E, int kind, const float* hyper, uint32_t* touched_to_clear /*nullable*/,
                    int64_t nwords, void* stream);
 /* Dense-semantics AdamW (every row decays, examples/dcn.py:127) reading its gradient from the compact rows:
- * rows whose touched bit is clear have g = 0; compact rows are re-zeroed and the bitmap is cleared afterwards. */
+ * rows whose touched bit is clear have g = 0; compact rows are re-zeroed and the bitmap is cleared afterwards.
+ * ever (nullable): the ever-touched bitmap of krs_adamw_cold, same meaning (ever |= touched is folded in). */
 int krs_adamw_compact(float* p, float* m, float* v, float* compact, uint32_t* touched, const uint32_t* wordprefix,
-                      const uint32_t* blockbase, int64_t n, int row_len, float lr, float b1, float b2, float eps,
-                      float wd, int64_t step, void* stream);
+                      const uint32_t* blockbase, uint32_t* ever, int64_t n, int row_len, float lr, float b1, float b2,
+                      float eps, float wd, int64_t step, void* stream);
 
 /* ------------------------------------------------------------------ peer memory (setup only)
  * Row-sharded tables live in cudaMalloc'd arenas exported with cudaIpc so that the fused gather

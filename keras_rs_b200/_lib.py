@@ -114,7 +114,7 @@ _sig("krs_xchg_grad_pull", C.c_int, C.POINTER(KrsXchg), i32, C.c_void_p, C.c_voi
      C.c_void_p)
 _sig("krs_rows_apply", C.c_int, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p, C.c_void_p, i64, i32, i32,
      C.POINTER(C.c_float), C.c_void_p, i64, C.c_void_p)
-_sig("krs_adamw_compact", C.c_int, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p, C.c_void_p, C.c_void_p, i64, i32,
+_sig("krs_adamw_compact", C.c_int, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, i64, i32,
      C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, i64, C.c_void_p)
 _sig("krs_ipc_alloc", C.c_int, C.POINTER(C.c_void_p), C.c_size_t, C.c_void_p)
 _sig("krs_ipc_open", C.c_int, C.c_void_p, C.POINTER(C.c_void_p))

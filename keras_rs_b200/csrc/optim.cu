@@ -215,12 +215,22 @@ __global__ void __launch_bounds__(256) rows_apply_kernel(float* __restrict__ p, 
 __global__ void __launch_bounds__(256) adamw_compact_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
                                                             float* __restrict__ compact, const uint32_t* __restrict__ touched,
                                                             const uint32_t* __restrict__ wordprefix,
-                                                            const uint32_t* __restrict__ blockbase, int64_t n4, int row_len4,
+                                                            const uint32_t* __restrict__ blockbase,
+                                                            const uint32_t* __restrict__ ever, int64_t n4, int row_len4,
                                                             AdamArgs a) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t row = i / row_len4;
     const uint32_t word = touched[row >> 5];
     const bool hit = (word >> (row & 31)) & 1u;
+    if (ever != nullptr && !hit && !((ever[row >> 5] >> (row & 31)) & 1u)) {     // never-touched row: m = v = 0, decay only
+      float4 pc = reinterpret_cast<float4*>(p)[i];
+      pc.x = pc.x - pc.x * a.wd * a.lr;
+      pc.y = pc.y - pc.y * a.wd * a.lr;
+      pc.z = pc.z - pc.z * a.wd * a.lr;
+      pc.w = pc.w - pc.w * a.wd * a.lr;
+      reinterpret_cast<float4*>(p)[i] = pc;
+      continue;
+    }
     int64_t gi = 0;
     float4 gp = make_float4(0.f, 0.f, 0.f, 0.f);
     if (hit) {
@@ -373,8 +383,8 @@ extern "C" int krs_rows_apply(float* p, float* s1, float* s2, float* compact, co
 }
 
 extern "C" int krs_adamw_compact(float* p, float* m, float* v, float* compact, uint32_t* touched, const uint32_t* wordprefix,
-                                 const uint32_t* blockbase, int64_t n, int row_len, float lr, float b1, float b2, float eps,
-                                 float wd, int64_t step, void* stream) {
+                                 const uint32_t* blockbase, uint32_t* ever, int64_t n, int row_len, float lr, float b1, float b2,
+                                 float eps, float wd, int64_t step, void* stream) {
   KRS_REQUIRE(p && m && v && compact && touched && wordprefix && blockbase, "krs_adamw_compact: null argument");
   KRS_REQUIRE(n >= 0 && step >= 1 && row_len >= 4 && row_len % 4 == 0 && n % row_len == 0, "krs_adamw_compact: bad n / row_len / step");
   KRS_REQUIRE(aligned16(p) && aligned16(m) && aligned16(v) && aligned16(compact), "krs_adamw_compact: buffers must be 16-byte aligned");
@@ -384,8 +394,16 @@ extern "C" int krs_adamw_compact(float* p, float* m, float* v, float* compact, u
   a.alpha = (float)((double)lr * sqrt(1.0 - pow((double)b2, (double)step)) / (1.0 - pow((double)b1, (double)step)));
   const int64_t work = n / 4;
   const unsigned grid = (unsigned)krs::imax<int64_t>(1, krs::imin<int64_t>(ceil_div<int64_t>(work, 256), (int64_t)sm_count() * 32));
-  adamw_compact_kernel<<<grid, 256, 0, as_stream(stream)>>>(p, m, v, compact, touched, wordprefix, blockbase, work, row_len / 4, a);
+  cudaStream_t s = as_stream(stream);
+  adamw_compact_kernel<<<grid, 256, 0, s>>>(p, m, v, compact, touched, wordprefix, blockbase, ever, work, row_len / 4, a);
   KRS_LAUNCH_CHECK();
-  KRS_CUDA(cudaMemsetAsync(touched, 0, sizeof(uint32_t) * (size_t)ceil_div<int64_t>(n / row_len, 32), as_stream(stream)));
+  const int64_t nwords = ceil_div<int64_t>(n / row_len, 32);
+  if (ever != nullptr) {
+    fold_touched_kernel<<<(unsigned)krs::imax<int64_t>(1, krs::imin<int64_t>(ceil_div<int64_t>(nwords, 256), (int64_t)sm_count() * 8)), 256, 0, s>>>(
+        ever, touched, nwords);
+    KRS_LAUNCH_CHECK();
+  } else {
+    KRS_CUDA(cudaMemsetAsync(touched, 0, sizeof(uint32_t) * (size_t)nwords, s));
+  }
   return KRS_OK;
 }

@@ -66,14 +66,16 @@ class DLRM(torch.nn.Module):
             d.build((None, k)); k = d.units
 
     # ------------------------------------------------------------------ forward (model.py:175-212)
-    def forward(self, dense: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
+    def forward(self, dense: torch.Tensor, ids: torch.Tensor, sparse_arena: bool = False) -> torch.Tensor:
+        """sparse_arena=True: the tables' gradients go to their persistent arenas + touched bitmaps (row-sparse optimizer
+        updates, no (V, E) gradient is materialised) instead of dense `.grad` tensors."""
         if ids.dtype not in (torch.int32, torch.int64):
             ids = ids.to(torch.int32)
         h = dense
         for d in self.bottom_mlp:
             h = d(h)
         emb = ops.gather_concat([dict(table=self.tables[f], ids=ids[:, f], weights=None, combiner="sum") for f in range(self.F)],
-                                sparse_arena=False)                             # (B, F*E): lookup + concat in one kernel
+                                sparse_arena=sparse_arena)                      # (B, F*E): lookup + concat in one kernel
         if self.interaction == "dot":
             feats = [h] + [emb[:, f * self.E:(f + 1) * self.E] for f in range(self.F)]
             x = torch.cat([h, self.dot(feats)], dim=-1)
@@ -98,7 +100,7 @@ class DLRM(torch.nn.Module):
         """forward -> BCE (main.py:201-210) -> backward -> optimizer on every variable; returns the loss tensor."""
         params = self.parameters_list()
         optimizer.zero_grad(params)
-        pred = self.forward(dense, ids)
+        pred = self.forward(dense, ids, sparse_arena=True)
         loss = ops.loss_fn(pred, labels, "bce")
         loss.backward()
         optimizer.apply(params)

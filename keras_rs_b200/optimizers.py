@@ -119,9 +119,14 @@ class AdamW(Optimizer):
             self._rows_apply(p, cs, OPT_ADAM, [self.learning_rate, self.beta_1, self.beta_2, self.epsilon, self._alpha()],
                              st["m"], st["v"])
             return
+        ever = getattr(p, "_krs_ever", None)
+        if ever is not None and not getattr(p, "_krs_ever_owner", None) in (None, id(self)):
+            ever = None                     # the bitmap describes the moments of ONE optimizer instance
+        if ever is not None:
+            p._krs_ever_owner = id(self)
         check(lib.krs_adamw_compact(ptr(p), ptr(st["m"]), ptr(st["v"]), ptr(cs.compact), ptr(cs.touched), ptr(cs.wordprefix),
-                                    ptr(cs.blockbase), p.numel(), p.shape[-1], self.learning_rate, self.beta_1, self.beta_2,
-                                    self.epsilon, self.weight_decay, max(self.iterations, 1), stream()))
+                                    ptr(cs.blockbase), ptr(ever), p.numel(), p.shape[-1], self.learning_rate, self.beta_1,
+                                    self.beta_2, self.epsilon, self.weight_decay, max(self.iterations, 1), stream()))
 
     # ---- device-resident hyper-parameters (CUDA-graph replay of the step) ----
     def enable_device_hyper(self, device="cuda"):

@@ -175,6 +175,9 @@ class ShardedDCN(DCN):
         self.emb_grad = None                      # no table-sized gradient buffer in the sharded model
         self.emb_touched = None
         self.cg = CompactGrads(self.total_rows, self.E, 1, "cuda")
+        # rows that have ever received a gradient (AdamW sweeps the others with a decay-only update, krs_adamw_cold)
+        self.emb_ever = torch.zeros_like(self.cg.touched)
+        self.emb._krs_ever = self.emb_ever
 
     def tables(self):
         return [self.emb[self.row_off[f]:self.row_off[f] + local_vocab(v, self.rank_, self.world_)]

@@ -146,3 +146,48 @@ def time_cpu_baseline(B=65536, F=26, V=1_000_000, E=32, L=3, units=(192, 192), s
             break
     sec = sum(times) / len(times)
     return dict(value=B / sec, cores=threads, steps=len(times), warmup=min(warmup, s), ms_per_step=sec * 1e3, batch=B)
+
+
+def time_reference_arm(B=65536, F=26, V=1_000_000, E=32, L=3, units=(192, 192), steps=20, warmup=5, optimizer="adamw",
+                       threads=None, seed=1234, budget_s=240.0):
+    """`bench.py --impl reference`: EXACTLY `warmup` untimed + `steps` timed steps.  The first warm-up step runs the full
+    workload and is timed; if warmup + steps of them fit `budget_s` the whole run is full size.  Otherwise every step is
+    a bounded sample of the same workload: batch AND vocabulary shrunk by the same power-of-two factor, which keeps the
+    per-example cost (dense layers per example + the dense optimizer sweep per example, V*F*E/B) unchanged."""
+    threads = threads or usable_cores()
+    torch.set_num_threads(threads)
+
+    def build(scale):
+        b, v = max(int(B * scale), 64), max(int(V * scale), 64)
+        tables, cross, mlp = synthetic_c2(F, v, E, L, units, seed)
+        return TorchDCN(tables, cross, mlp, lr=0.01, optimizer=optimizer), b, v
+
+    g = torch.Generator().manual_seed(seed + 1)
+
+    def one(model, b, v):
+        ids = torch.randint(0, v, (b, F), generator=g)
+        y = torch.rand((b,), generator=g)
+        t0 = time.perf_counter()
+        model.train_step(ids, y)
+        return time.perf_counter() - t0
+
+    model, b, v = build(1.0)
+    t1 = one(model, b, v)
+    done_warm = 1
+    scale = 1.0
+    need = t1 * (steps + max(warmup, 1) - 1)
+    if need > budget_s:
+        while scale > 1.0 / 4096 and t1 * scale * (steps + warmup) > budget_s:
+            scale /= 2
+        del model
+        model, b, v = build(scale)
+        done_warm = 0
+    for _ in range(max(warmup - done_warm, 0)):
+        one(model, b, v)
+    times = [one(model, b, v) for _ in range(steps)]
+    sec = sum(times) / len(times)
+    sample = (f"every step = the full batch of {B} examples over the full {F} x {V}-row tables" if scale == 1.0 else
+              f"every step = a 1/{int(round(1 / scale))} sample: batch {b} over {F} x {v}-row tables (batch and vocabulary shrunk "
+              f"together so the per-example cost incl. the dense optimizer sweep is unchanged; one full-size step took {t1:.1f} s)")
+    return dict(value=b / sec, cores=threads, steps=steps, warmup=warmup, ms_per_step=sec * 1e3, batch=b, vocab=v, scale=scale,
+                sample=sample, full_step_s=t1)

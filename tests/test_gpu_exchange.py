@@ -52,10 +52,11 @@ def test_route_request_lists_bit_exact(K, S, idt):
     d_ids = dev(ids, idt)
     ws = torch.zeros((int(lib.krs_xchg_route_workspace_bytes(B, F, S)) // 4 + 1,), dtype=torch.int32, device="cuda")
     x0 = lay.view(region, lay.off_x0, (B * F, E), torch.float32)
+    d_vocab, d_offs = dev(np.array(vocab), torch.int64), dev(np.array(offs).reshape(-1), torch.int32)
     for parity in (0, 1):
         x0.fill_(1.0)
-        check(lib.krs_xchg_route(C.byref(x), parity, ptr(d_ids), int(idt == torch.int64), F, ptr(dev(np.array(vocab), torch.int64)),
-                                 ptr(dev(np.array(offs).reshape(-1), torch.int32)), ptr(ws), 1, stream()))
+        check(lib.krs_xchg_route(C.byref(x), parity, ptr(d_ids), int(idt == torch.int64), F, ptr(d_vocab), ptr(d_offs), ptr(ws), 1,
+                                 stream()))
         hdr = npy(lay.view(region, lay.off_hdr, (2, XCHG_MAX_SHARDS + 1), torch.int32))[parity]
         rows = npy(lay.view(region, lay.off_rows, (2, B * F), torch.int32))[parity]
         pos = npy(lay.view(region, lay.off_pos, (2, B * F), torch.int32))[parity]
