@@ -626,6 +626,25 @@ def sharded_phases(model, opt, dev_ids, dev_y, B, denom, world, dist):
     out["nvlink_GBps_gather_push"] = round(P * row_bytes * remote / max(out["owner_gather_push"], 1e-9) * 1e-6, 1)
     out["nvlink_GBps_grad_pull"] = round(P * row_bytes * remote / max(out["slot_scan+grad_pull"], 1e-9) * 1e-6, 1)
     out["sum"] = round(sum(acc.values()), 4)
+    if dist is not None:
+        # baseline: NCCL's own all-to-all (grouped send/recv) moving the SAME bytes (P rows of E floats, equal splits) —
+        # only the transfer; a NCCL-based exchange would still need the gather before and the scatter / unpermute after it
+        P2 = P // world * world
+        src = torch.empty((P2, model.E), device="cuda")
+        dst = torch.empty_like(src)
+        for _ in range(2):
+            dist.all_to_all_single(dst, src)
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0 = ev()
+        for _ in range(reps):
+            dist.all_to_all_single(dst, src)
+        e1 = ev()
+        torch.cuda.synchronize()
+        tt = torch.tensor([e0.elapsed_time(e1) / reps], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        out["nccl_all_to_all_same_bytes_ms"] = round(float(tt), 4)
+        out["nccl_all_to_all_GBps"] = round(P2 * row_bytes * remote / max(float(tt), 1e-9) * 1e-6, 1)
     return out
 
 

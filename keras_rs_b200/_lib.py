@@ -13,7 +13,6 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libkrs_b200.so")
-NCCL_LIB_PATH = os.path.join(_HERE, "lib", "libkrs_b200_nccl.so")
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
@@ -132,8 +131,6 @@ EXPORTED = [
     "krs_slot_scan", "krs_xchg_grad_pull", "krs_rows_apply", "krs_adamw_compact", "krs_ipc_alloc", "krs_ipc_open",
     "krs_ipc_close", "krs_ipc_free", "krs_enable_peer_access",
 ]
-NCCL_EXPORTED = ["krs_nccl_unique_id", "krs_nccl_init", "krs_nccl_destroy", "krs_nccl_all_to_all_v",
-                 "krs_nccl_all_reduce_sum_f32"]
 
 ACT = {None: 0, "linear": 0, "relu": 1, "sigmoid": 2, "tanh": 3, "swish": 4, "silu": 4}
 COMBINER = {"sum": 0, "mean": 1, "sqrtn": 2}
@@ -170,22 +167,3 @@ def require_cuda(t: torch.Tensor, name: str, dtype=torch.float32) -> torch.Tenso
     return t
 
 
-_nccl_lib = None
-
-
-def nccl_lib():
-    """libkrs_b200_nccl.so, loaded lazily (multi-GPU only)."""
-    global _nccl_lib
-    if _nccl_lib is None:
-        if not os.path.exists(NCCL_LIB_PATH):
-            raise ImportError(f"keras_rs_b200: {NCCL_LIB_PATH} is missing (build it first)")
-        n = C.CDLL(NCCL_LIB_PATH)
-        n.krs_nccl_last_error.restype = C.c_char_p
-        n.krs_nccl_unique_id.argtypes = [C.c_void_p]
-        n.krs_nccl_init.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, i32, i32]
-        n.krs_nccl_destroy.argtypes = [C.c_void_p]
-        n.krs_nccl_all_to_all_v.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(i64), C.POINTER(i64),
-                                            C.c_void_p, C.POINTER(i64), C.POINTER(i64), i32, C.c_void_p]
-        n.krs_nccl_all_reduce_sum_f32.argtypes = [C.c_void_p, C.c_void_p, i64, C.c_void_p]
-        _nccl_lib = n
-    return _nccl_lib

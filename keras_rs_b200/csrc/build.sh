@@ -1,5 +1,5 @@
 #!/bin/bash
-# Builds libkrs_b200.so (+ libkrs_b200_nccl.so) for sm_100a, in-tree.
+# Builds libkrs_b200.so for sm_100a, in-tree.
 set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 OUT="$HERE/../lib"
@@ -20,7 +20,4 @@ for p in "${pids[@]:-}"; do [ -n "$p" ] && wait "$p"; done
 OBJS=()
 for s in "${SRCS[@]}"; do OBJS+=("$HERE/obj/$s.o"); done
 "$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT/libkrs_b200.so" "${OBJS[@]}" -lcudart
-if [ ! -f "$OUT/libkrs_b200_nccl.so" ] || [ "$HERE/nccl_a2a.cu" -nt "$OUT/libkrs_b200_nccl.so" ]; then
-  "$NVCC" "${FLAGS[@]}" -shared "$HERE/nccl_a2a.cu" -o "$OUT/libkrs_b200_nccl.so" -lnccl > "$HERE/obj/nccl.log" 2>&1 || { cat "$HERE/obj/nccl.log"; exit 1; }
-fi
 echo "built $OUT/libkrs_b200.so"

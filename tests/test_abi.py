@@ -25,23 +25,9 @@ def test_header_declares_expected_entry_points():
 def test_library_exports_every_declared_symbol():
     from keras_rs_b200 import _lib
     main = ctypes.CDLL(_lib.LIB_PATH)
-    nccl_syms = [s for s in header_symbols() if s.startswith("krs_nccl_")]
     for s in header_symbols():
-        if s in nccl_syms:
-            continue
         assert hasattr(main, s), f"{s} declared in krs_b200.h but not exported by libkrs_b200.so"
-    assert sorted(_lib.EXPORTED) == sorted(s for s in header_symbols() if s not in nccl_syms)
-    assert sorted(_lib.NCCL_EXPORTED) == sorted(nccl_syms)
-
-
-def test_nccl_library_exports():
-    from keras_rs_b200 import _lib
-    try:
-        n = ctypes.CDLL(_lib.NCCL_LIB_PATH)
-    except OSError as e:
-        pytest.skip(f"libnccl not loadable here: {e}")
-    for s in _lib.NCCL_EXPORTED:
-        assert hasattr(n, s)
+    assert sorted(_lib.EXPORTED) == sorted(header_symbols())
 
 
 def test_version_and_error_string():

@@ -56,6 +56,33 @@ def _worker(rank, world, port, q):
     for d in alls:
         merged.update(d)
     ok &= all(np.array_equal(merged[int(i)], table[int(i)]) for i in ids)
+    # the routed protocol of csrc/exchange.cu, emulated with the oracle: every rank builds request lists for its own ids,
+    # owners serve the rows of their shard, activations land at the requested positions; gradients flow back the same way
+    vocab2 = [37, 64, 5]
+    tabs = [np.arange(v * 2, dtype=np.float32).reshape(v, 2) + 1000 * f for f, v in enumerate(vocab2)]
+    offs_all = [shard_row_offsets(vocab2, o, world)[0] for o in range(world)]
+    my_ids = np.stack([np.random.default_rng(10 + rank).integers(-v, v, size=9) for v in vocab2], axis=1)
+    rows, pos = O.route_requests(my_ids, vocab2, world, offs_all)
+    reqs = [None] * world
+    dist.all_gather_object(reqs, (rows, pos))
+    arena = np.zeros((shard_row_offsets(vocab2, rank, world)[1], 2), np.float32)
+    for f, t_ in enumerate(tabs):
+        sh = O.mod_shard_table(t_, world)[rank]
+        arena[offs_all[rank][f]:offs_all[rank][f] + len(sh)] = sh
+    served = [(arena[reqs[r][0][rank]], reqs[r][1][rank]) for r in range(world)]        # what I send to requester r
+    got = [None] * world
+    dist.all_gather_object(got, served)
+    x0 = np.full((9 * len(vocab2), 2), np.nan, np.float32)
+    for o in range(world):
+        vals, where = got[o][rank]
+        x0[where] = vals
+    ref = np.concatenate([O.embedding_lookup(t_, my_ids[:, f]) for f, t_ in enumerate(tabs)], axis=1).reshape(9 * len(vocab2), 2)
+    ok &= bool(np.array_equal(x0, ref))
+    from keras_rs_b200.sharded import RegionLayout
+    lay = RegionLayout(9, len(vocab2), 4)
+    lays = [None] * world
+    dist.all_gather_object(lays, [lay.off_flags, lay.off_hdr, lay.off_rows, lay.off_pos, lay.off_x0, lay.off_grad, lay.nbytes])
+    ok &= all(l == lays[0] for l in lays) and lay.off_x0 % 256 == 0 and lay.off_grad % 256 == 0
     t = torch.tensor([1.0 if ok else 0.0])
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
