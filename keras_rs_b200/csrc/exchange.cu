@@ -219,7 +219,7 @@ struct OwnerArgs {
 struct OwnerCtaState {
   int start[MAXS];      // first entry of my bucket inside requester r's lists
   int count[MAXS];
-  int chunk0[MAXS + 1]; // first 32-entry chunk of requester r
+  int chunk0[MAXS + 1]; // first 32-entry chunk of stage k (requester (me + k) % S)
 };
 
 __device__ __forceinline__ void owner_prologue(const OwnerArgs& a, OwnerCtaState& st) {
@@ -230,9 +230,12 @@ __device__ __forceinline__ void owner_prologue(const OwnerArgs& a, OwnerCtaState
     st.count[threadIdx.x] = s1 - s0;
   }
   __syncthreads();
+  // Requesters are served in ROTATED order, stage k = requester (me + k) % S: all owners run their stages roughly in
+  // lockstep, so with the plain order 0, 1, 2 ... every GPU of the box would push to (pull from) the same peer at the
+  // same time and that peer's NVLink ingress (egress) would be the whole system's bandwidth.
   if (threadIdx.x == 0) {
     int run = 0;
-    for (int r = 0; r < a.S; ++r) { st.chunk0[r] = run; run += (st.count[r] + 31) >> 5; }
+    for (int k = 0; k < a.S; ++k) { st.chunk0[k] = run; run += (st.count[(a.me + k) % a.S] + 31) >> 5; }
     st.chunk0[a.S] = run;
   }
   __syncthreads();
@@ -252,9 +255,10 @@ __global__ void __launch_bounds__(256) gather_push_kernel(const OwnerArgs a) {
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int total = st.chunk0[a.S];
   for (int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < total; c += nwarps) {
-    int r = 0;
-    while (c >= st.chunk0[r + 1]) ++r;
-    const int j = ((c - st.chunk0[r]) << 5) + lane;
+    int k = 0;
+    while (c >= st.chunk0[k + 1]) ++k;
+    const int r = (a.me + k) % a.S;
+    const int j = ((c - st.chunk0[k]) << 5) + lane;
     const float* src = nullptr;
     float* dst = nullptr;
     if (j < st.count[r]) {
@@ -376,9 +380,10 @@ __global__ void __launch_bounds__(256) grad_pull_kernel(const OwnerArgs a) {
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int total = st.chunk0[a.S];
   for (int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < total; c += nwarps) {
-    int r = 0;
-    while (c >= st.chunk0[r + 1]) ++r;
-    const int j = ((c - st.chunk0[r]) << 5) + lane;
+    int k = 0;
+    while (c >= st.chunk0[k + 1]) ++k;
+    const int r = (a.me + k) % a.S;
+    const int j = ((c - st.chunk0[k]) << 5) + lane;
     int32_t row = -1 - lane;
     const float* src = nullptr;
     float* dst = nullptr;

@@ -35,7 +35,7 @@ class DCN(torch.nn.Module):
     def __init__(self, vocab_sizes: Sequence[int], embedding_dim: int = 32, num_cross_layers: int = 3,
                  projection_dim: int | None = None, dense_units: Sequence[int] = (192, 192),
                  diag_scale: float = 0.0, pre_activation=None, loss: str = "mse", seed: int = 0,
-                 device: str = "cuda", embeddings_initializer="uniform"):
+                 device: str = "cuda", embeddings_initializer="uniform", dense_activation: str = "relu"):
         super().__init__()
         self.vocab_sizes = [int(v) for v in vocab_sizes]
         self.F = len(self.vocab_sizes)
@@ -55,7 +55,7 @@ class DCN(torch.nn.Module):
                          name=f"cross_{i}")
             for i in range(self.L)])
         units = list(dense_units) + [1]
-        acts = ["relu"] * len(dense_units) + [None]
+        acts = [dense_activation] * len(dense_units) + [None]      # examples/dcn.py:445 uses relu
         self.mlp = torch.nn.ModuleList([
             Dense(u, activation=a, kernel_initializer=initializers.GlorotUniform(seed=seed + 101 + i), device=device,
                   name=f"dense_{i}")

@@ -116,7 +116,7 @@ def test_sharded_step_matches_oracle_on_the_global_batch(K, world, E, idt, opt_n
     vocabularies smaller than the shard count."""
     from keras_rs_b200.sharded import SimGroup
     vocab, Bl, steps = [50, 33, 64, 7, 3], 96, 3
-    g = SimGroup(vocab, world, embedding_dim=E, num_cross_layers=2, dense_units=(16,), seed=5)
+    g = SimGroup(vocab, world, embedding_dim=E, num_cross_layers=2, dense_units=(16,), seed=5, dense_activation="tanh")
     for m in g.ranks[1:]:                                   # data-parallel replicas start from identical dense weights
         m.dense_flat.copy_(g.ranks[0].dense_flat)
     m0 = g.ranks[0]
@@ -155,6 +155,55 @@ def test_sharded_step_matches_oracle_on_the_global_batch(K, world, E, idt, opt_n
         assert_close(npy(preds[r]), ref[r * 8:(r + 1) * 8], rel=1e-5, what="sharded predict",
                      scale=max(float(np.abs(ref).max()), 1e-3))
         assert int(g.ranks[r].cg.touched.abs().max()) == 0
+
+
+@pytest.mark.parametrize("world,E", [(2, 32), (4, 128), (8, 32), (8, 8), (3, 48)])
+def test_compact_gradient_rows_match_oracle(K, world, E):
+    """The owner-side compact gradient rows (after grad_pull, before any optimizer) against the oracle's dense table
+    gradients of the GLOBAL batch, relative to max|g| — the direct check of the exchange's backward: SGD / Adagrad updates
+    at lr = 0.01 are too small against the parameter scale to expose a wrong gradient row."""
+    from keras_rs_b200._lib import stream
+    from keras_rs_b200.sharded import SimGroup
+    from keras_rs_b200.sharding import local_vocab
+    vocab, Bl = [1000, 777, 64, 7], 256
+    g = SimGroup(vocab, world, embedding_dim=E, num_cross_layers=2, dense_units=(16,), seed=7, dense_activation="tanh")
+    m0 = g.ranks[0]
+    P = PAR.params_of(_global_tables(g, vocab), m0.cross, m0.mlp)
+    gids, gy = PAR.make_batches(vocab, Bl, world, 1, seed=77, bad_ids=True)[0]
+    cache = {}
+    pred = O.dcn_forward(P, gids, cache)
+    _, dpred = O.mse_loss(pred, gy)
+    og = O.dcn_backward(P, gids, dpred, cache)
+    bs, s = g._wire(Bl), stream()
+    for r, (m, b) in enumerate(zip(g.ranks, bs)):
+        b["ids"].copy_(dev(gids[r * Bl:(r + 1) * Bl]))
+        b["labels"].copy_(dev(gy[r * Bl:(r + 1) * Bl]))
+        m._route(b, Bl, s)
+    for m, b in zip(g.ranks, bs):
+        m._serve(b, s, train=True)
+    curs = [m._dense_step(b, Bl, Bl * world, s) for m, b in zip(g.ranks, bs)]
+    for r, cur in enumerate(curs):         # activation gradient of every rank's slice first (names the failing side)
+        ref = np.concatenate([og["x0"][r * Bl:(r + 1) * Bl]], axis=0) if "x0" in og else None
+        if ref is not None:
+            assert_close(npy(cur), ref, rel=1e-5, what=f"rank {r} dL/dx0")
+    for m, b, cur in zip(g.ranks, bs, curs):
+        m._scatter_from(b, Bl, cur, s)
+    g.check_errors()
+    for r, m in enumerate(g.ranks):
+        nu = int(m.cg.n_unique.item())
+        rows = m.cg.uniq_rows[:nu].cpu().numpy()
+        assert (np.diff(rows) > 0).all()                       # slots are numbered in arena-row order
+        dense = np.zeros((m.total_rows, E), np.float32)
+        dense[rows] = npy(m.cg.compact[:nu])
+        looked_up = 0
+        for f, v in enumerate(vocab):
+            lv = local_vocab(v, r, world)
+            ref = og["tables"][f][r::world]
+            assert_close(dense[m.row_off[f]:m.row_off[f] + lv], ref, rel=1e-5, what=f"rank {r} table {f} gradient rows",
+                         scale=max(float(np.abs(og["tables"][f]).max()), 1e-30))
+            idx, ok = O.resolve_ids(gids[:, f], v)
+            looked_up += len(set(int(i) for i in idx[ok] if i % world == r))
+        assert nu == looked_up                                  # one compact row per distinct looked-up row
 
 
 def _train_split(g, ids_r, y_r, table_opts, dense_opts, denom):
