@@ -81,6 +81,43 @@ def bench_gather128(reps):
     return res
 
 
+# examples/ml_perf/configs/v6e_8.py:15-172: vocabulary sizes and feature_list_length (hotness) of the 26 sparse features
+MLPERF_VOCAB = [40000000, 39060, 17295, 7424, 20265, 3, 7122, 1543, 63, 40000000, 3067956, 405282, 10, 2209, 11938, 155, 4, 976, 14,
+                40000000, 40000000, 40000000, 590152, 12973, 108, 36]
+MLPERF_HOT = [3, 2, 1, 2, 6, 1, 1, 1, 1, 7, 3, 8, 1, 6, 9, 5, 1, 1, 1, 12, 100, 27, 10, 3, 1, 1]
+
+
+def bench_multihot(reps):
+    """Fused multi-table MULTI-HOT gather on the ml_perf feature list (sum of hotness 214, combiner sum, int64 ids as
+    examples/ml_perf/dataloader.py:93-98 produces them), E = 128, batch 65536.  Vocabularies above 2e6 rows are capped at
+    2e6 (the 40M-row tables would need 20 GB each); rows stay far larger than L2 either way."""
+    E, B = 128, 65536
+    g = torch.Generator(device="cuda").manual_seed(2)
+    vocab = [min(v, 2_000_000) for v in MLPERF_VOCAB]
+    tables = [torch.rand((v, E), device="cuda", generator=g) for v in vocab]
+    res = []
+    feats = []
+    for f, (v, h) in enumerate(zip(vocab, MLPERF_HOT)):
+        ids = torch.randint(0, v, (B, h), device="cuda", generator=g)            # int64
+        feats.append(dict(table=tables[f], ids=ids if h > 1 else ids[:, 0], combiner="sum"))
+    plan = K.ops.GatherPlan(feats)
+    out = torch.empty((B, len(vocab) * E), device="cuda")
+    ms = timed(lambda i: plan.forward(out), reps)
+    n_lookups = B * sum(MLPERF_HOT)
+    by = n_lookups * E * 4 + B * len(vocab) * E * 4 + n_lookups * 8
+    res.append(dict(kernel="gather_generic_kernel (multi-hot)", config=f"ml_perf 26 features, sum(H)=214, E=128, B={B}, int64 ids, sum",
+                    ms=ms, GBps=by / ms * 1e-6, bytes=by, frac_of_measured_hbm=by / ms * 1e-6 / peaks()["hbm_gbs"]))
+    # backward (scatter-add of the (B, F*E) gradient into the 214 rows of every sample)
+    grads = [torch.zeros_like(t) for t in tables]
+    touched = [torch.zeros(((t.shape[0] + 31) // 32,), dtype=torch.int32, device="cuda") for t in tables]
+    gout = torch.randn((B, len(vocab) * E), device="cuda", generator=g)
+    ms_b = timed(lambda i: plan.backward(gout, grads, touched), max(3, reps // 2))
+    by_b = B * len(vocab) * E * 4 + 2 * n_lookups * E * 4 + n_lookups * 8
+    res.append(dict(kernel="scatter_generic_kernel (multi-hot)", config="same", ms=ms_b, GBps=by_b / ms_b * 1e-6, bytes=by_b,
+                    frac_of_measured_hbm=by_b / ms_b * 1e-6 / peaks()["hbm_gbs"]))
+    return res
+
+
 def bench_topk(reps):
     nq, nc, d, k = 4096, 10_000_000, 64, 100
     g = torch.Generator(device="cuda").manual_seed(42)
@@ -103,7 +140,7 @@ def main():
     ap.add_argument("--what", default="dot,gather128,topk")
     ap.add_argument("--reps", type=int, default=10)
     a = ap.parse_args()
-    fns = {"dot": bench_dot, "gather128": bench_gather128, "topk": bench_topk}
+    fns = {"dot": bench_dot, "gather128": bench_gather128, "topk": bench_topk, "multihot": bench_multihot}
     for w in a.what.split(","):
         for r in fns[w](a.reps):
             print(json.dumps(r), flush=True)

@@ -36,9 +36,12 @@ __device__ __forceinline__ uint32_t tf32_rna(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return r;
 }
+// 3xTF32 split with plain integer / fp32 ops: hi = x truncated to TF32, lo = (x - hi) rounded to TF32 by adding half an
+// ulp of the 13 dropped bits.  cvt.rna.tf32.f32 is emulated with ~4 instructions on sm_100a and this kernel splits every
+// element it reads (the split was ~40 % of its issue slots); the residual x - hi is exact, so the pair keeps ~21 bits.
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  hi = tf32_rna(x);
-  lo = tf32_rna(x - __uint_as_float(hi));
+  hi = __float_as_uint(x) & 0xFFFFE000u;
+  lo = (__float_as_uint(x - __uint_as_float(hi)) + 0x1000u) & 0xFFFFE000u;
 }
 __device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
                                          uint32_t b1) {
@@ -53,6 +56,10 @@ __device__ __forceinline__ int tri_index(int i, int j, int self) { return self ?
 // ------------------------------------------------------------------ forward (mma path)
 // N <= 32, E % 16 == 0, every feature pointer 16-byte aligned with stride % 4 == 0.
 __global__ void __launch_bounds__(128) dot_fwd_mma_kernel(const __grid_constant__ DotParams p) {
+  // per-warp staging of one sample's outputs: the selected triangle is written to global memory as ONE contiguous run
+  // (out_dim floats, full 128-byte lines) instead of 351 scattered 4-byte stores (the forward was store-bound: 48 % of HBM)
+  __shared__ float stage[4][32 * 32];
+  float* st = stage[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -105,6 +112,10 @@ __global__ void __launch_bounds__(128) dot_fwd_mma_kernel(const __grid_constant_
       for (int i = 0; i < 4; ++i) x[i] = xn[i];
     }
     float* o = p.out + b * (int64_t)p.out_dim;
+    __syncwarp();                              // the previous sample's staged row has been read
+    if (p.skip_gather)                         // N x N layout: entries above the kept triangle are exact zeros
+      for (int idx = lane; idx < p.out_dim; idx += 32) st[idx] = 0.f;
+    __syncwarp();
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -115,11 +126,13 @@ __global__ void __launch_bounds__(128) dot_fwd_mma_kernel(const __grid_constant_
           const int i = 16 * mt + g + ((q & 2) ? 8 : 0);
           const int j = 8 * nt + 2 * t + (q & 1);
           if (i < N && j < N && (j < i || (self && j == i))) {
-            if (p.skip_gather) o[i * N + j] = acc[mt][nt][q];
-            else o[tri_index(i, j, self)] = acc[mt][nt][q];
+            if (p.skip_gather) st[i * N + j] = acc[mt][nt][q];
+            else st[tri_index(i, j, self)] = acc[mt][nt][q];
           }
         }
       }
+    __syncwarp();
+    for (int idx = lane; idx < p.out_dim; idx += 32) __stcs(o + idx, st[idx]);
   }
 }
 
@@ -128,13 +141,17 @@ __global__ void __launch_bounds__(128) dot_fwd_mma_kernel(const __grid_constant_
 // Requirements: N <= 32, E % 32 == 0, 16-byte aligned rows.
 __global__ void __launch_bounds__(128) dot_bwd_mma_kernel(const __grid_constant__ DotParams p) {
   __shared__ float S[4][32][33];
+  __shared__ float G[4][32 * 32];          // the sample's incoming gradient, loaded with coalesced 128-byte reads
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int N = p.N, E = p.E, self = p.self_interaction;
   float(*Sw)[33] = S[warp];
   for (int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < p.B; b += nwarps) {
-    const float* go = p.gout + b * (int64_t)p.out_dim;
+    const float* gsrc = p.gout + b * (int64_t)p.out_dim;
+    float* go = G[warp];
+    __syncwarp();
+    for (int idx = lane; idx < p.out_dim; idx += 32) go[idx] = __ldcs(gsrc + idx);
     __syncwarp();
     for (int idx = lane; idx < 32 * 32; idx += 32) {
       const int i = idx >> 5, j = idx & 31;
@@ -295,7 +312,6 @@ extern "C" int krs_dot_fwd(const float* const* feats, const int64_t* strides, in
   if (B == 0 || p.out_dim == 0) return KRS_OK;
   cudaStream_t s = as_stream(stream);
   if ((E % 16 == 0) && rows_vec_ok(p, false)) {
-    if (skip_gather) KRS_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)B * p.out_dim, s));
     const unsigned grid = (unsigned)krs::imax<int64_t>(1, krs::imin<int64_t>(ceil_div<int64_t>(B, 4), (int64_t)sm_count() * 16));
     dot_fwd_mma_kernel<<<grid, 128, 0, s>>>(p);
   } else {

@@ -276,23 +276,44 @@ __global__ void __launch_bounds__(256) gather_generic_kernel(const __grid_consta
       float acc[W];
 #pragma unroll
       for (int j = 0; j < W; ++j) acc[j] = 0.f;
-      for (int h = 0; h < H; ++h) {
-        const int64_t idx = b * ft.ids_stride + h;
-        const int64_t id = resolve_id(ft.ids_i64 ? load_id<int64_t>(ft.ids, idx) : load_id<int32_t>(ft.ids, idx), ft.vocab);
-        const float w = use_w ? ft.weights[idx] : 1.f;
-        float v[W];
-        if (id < 0) {                        // no such row: NaN (jnp.take "fill"), which poisons the reduced sample
+      // Multi-hot rows (ml_perf hotness up to 100, examples/ml_perf/configs/v6e_8.py): HU row loads are in flight per lane
+      // group before the first is consumed; the sum itself stays sequential in h (bit-exact against the oracle's order).
+      constexpr int HU = 8;
+      for (int h0 = 0; h0 < H; h0 += HU) {
+        const float* src[HU];
+        float w[HU];
+        float v[HU][W];
 #pragma unroll
-          for (int j = 0; j < W; ++j) v[j] = __int_as_float(0x7fc00000);
-        } else if (VEC) {
-          float4 t = ldg_nc_f4(row_ptr(ft, id) + c * W);
-          v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-        } else {
-          v[0] = __ldg(row_ptr(ft, id) + c * W);
+        for (int u = 0; u < HU; ++u) {
+          src[u] = nullptr;
+          w[u] = 1.f;
+          if (h0 + u < H) {
+            const int64_t idx = b * ft.ids_stride + h0 + u;
+            const int64_t id = resolve_id(ft.ids_i64 ? load_id<int64_t>(ft.ids, idx) : load_id<int32_t>(ft.ids, idx), ft.vocab);
+            if (use_w) w[u] = ft.weights[idx];
+            src[u] = id < 0 ? nan_row() : row_ptr(ft, id) + c * W;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < HU; ++u) {
+          if (src[u] == nullptr) continue;
+          if (src[u] == nan_row()) {               // no such row: NaN (jnp.take "fill"), which poisons the reduced sample
+#pragma unroll
+            for (int j = 0; j < W; ++j) v[u][j] = __int_as_float(0x7fc00000);
+          } else if (VEC) {
+            const float4 t = ldg_nc_f4(src[u]);
+            v[u][0] = t.x; v[u][1] = t.y; v[u][2] = t.z; v[u][3] = t.w;
+          } else {
+            v[u][0] = __ldg(src[u]);
+          }
         }
         // x = x * w ; sum over axis -2 in order h = 0..H-1 (no FMA contraction: embed_reduce.py:253,261)
 #pragma unroll
-        for (int j = 0; j < W; ++j) acc[j] = (H == 1) ? __fmul_rn(v[j], w) : __fadd_rn(acc[j], __fmul_rn(v[j], w));
+        for (int u = 0; u < HU; ++u) {
+          if (src[u] == nullptr) continue;
+#pragma unroll
+          for (int j = 0; j < W; ++j) acc[j] = (H == 1) ? __fmul_rn(v[u][j], w[u]) : __fadd_rn(acc[j], __fmul_rn(v[u][j], w[u]));
+        }
       }
       if (ft.reduce && ft.combiner != KRS_COMBINER_SUM) {
 #pragma unroll

@@ -724,9 +724,38 @@ __global__ void __launch_bounds__(256) split_lo_kernel(const float4* __restrict_
 // caller-owned scratch for the precomputed B_lo plane (krs_gemm_set_workspace); calls that use it must be issued
 // on one stream at a time
 struct Workspace { void* ptr; size_t bytes; int device; };
+constexpr int MAX_DEVICES = 64;
 std::mutex g_ws_mu;
-Workspace g_ws_val{nullptr, 0, -1};
-Workspace get_ws() { std::lock_guard<std::mutex> l(g_ws_mu); return g_ws_val; }
+Workspace g_ws_val[MAX_DEVICES];           // one registration per device (a process may drive several GPUs)
+Workspace get_ws(int dev) {
+  std::lock_guard<std::mutex> l(g_ws_mu);
+  return (dev >= 0 && dev < MAX_DEVICES) ? g_ws_val[dev] : Workspace{nullptr, 0, -1};
+}
+
+// debug / tuning overrides, read ONCE per process (they used to cost ~10 getenv calls per GEMM launch)
+struct EnvKnobs {
+  int no_mask = 1, mn_layout = 1, mn_swz = (int)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, mn_lbo = 2048, mn_sbo = 512, mn_kstep = 1024;
+  int fuse_n = 1, b_lo_tma = 1, allow3d = 1;
+  uint32_t wait_ns = 0x400;
+};
+const EnvKnobs& env_knobs() {
+  static EnvKnobs k;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    auto geti = [](const char* name, int& v) { if (const char* e = getenv(name)) v = atoi(e); };
+    geti("KRS_TC_NO_MASK", k.no_mask);
+    geti("KRS_TC_MN_LAYOUT", k.mn_layout);
+    geti("KRS_TC_MN_SWZ", k.mn_swz);
+    geti("KRS_TC_MN_LBO", k.mn_lbo);
+    geti("KRS_TC_MN_SBO", k.mn_sbo);
+    geti("KRS_TC_MN_KSTEP", k.mn_kstep);
+    geti("KRS_TC_FUSE_N", k.fuse_n);
+    geti("KRS_TC_B_LO_TMA", k.b_lo_tma);
+    if (const char* e = getenv("KRS_TC_WAIT_NS")) k.wait_ns = (uint32_t)atoi(e);
+    if (getenv("KRS_TC_NO_3D") != nullptr) k.allow3d = 0;
+  });
+  return k;
+}
 
 // ---------------------------------------------------------------- host side
 // MN-contiguous matrix [rows = K][cols = MN] viewed as 3-D {32, K, MN/32}: one box {32, BK, blocks} lands in
@@ -815,33 +844,25 @@ int gemm_tc(const float* A, int64_t lda, bool transA, const float* B, int64_t ld
   // the tensor core ignores the low 13 mantissa bits of a tf32 operand: leaving hi = raw fp32 is bit-identical
   // to masking it (tests/tc_stress.py, both modes) and saves a third of the converter's shared-memory stores
   g.trace = g_trace.load();
-  g.no_mask = 1;
-  if (const char* e = getenv("KRS_TC_NO_MASK")) g.no_mask = atoi(e);
-  g.mn_lbo = 2048; g.mn_sbo = 512; g.mn_kstep = 1024; g.mn_layout = 1;
-  int mn_swz = (int)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
-  if (const char* e = getenv("KRS_TC_MN_LAYOUT")) g.mn_layout = atoi(e);
-  if (const char* e = getenv("KRS_TC_MN_SWZ")) mn_swz = atoi(e);
-  if (const char* e = getenv("KRS_TC_MN_LBO")) g.mn_lbo = atoi(e);       // debug overrides
-  if (const char* e = getenv("KRS_TC_MN_SBO")) g.mn_sbo = atoi(e);
-  if (const char* e = getenv("KRS_TC_MN_KSTEP")) g.mn_kstep = atoi(e);
-  g.fuse_n = 1;
-  if (const char* e = getenv("KRS_TC_FUSE_N")) g.fuse_n = atoi(e);
+  const EnvKnobs& env = env_knobs();
+  g.no_mask = env.no_mask;
+  g.mn_lbo = env.mn_lbo; g.mn_sbo = env.mn_sbo; g.mn_kstep = env.mn_kstep; g.mn_layout = env.mn_layout;
+  const int mn_swz = env.mn_swz;
+  g.fuse_n = env.fuse_n;
   if (2 * g.bn > 256) g.fuse_n = 0;
   // B_lo plane precomputed once per call into the caller-registered workspace when B is small and re-read by many
   // m-tiles (weights): the converters then touch only the A tile (28 -> 16 elements and 10 -> 4 shared-memory
   // instructions per thread and k-block in VER 2)
-  g.wait_ns = 0x400;
-  if (const char* e = getenv("KRS_TC_WAIT_NS")) g.wait_ns = (uint32_t)atoi(e);
+  g.wait_ns = env.wait_ns;
   g.b_lo_tma = 0;
   const float* B_lo = nullptr;
   {
     const int64_t b_rows = transB ? N : K;
     const size_t b_plane = (size_t)b_rows * (size_t)ldb * sizeof(float);
-    Workspace w = get_ws();
     int cur_dev = -1;
-    bool want = w.ptr != nullptr && b_plane <= w.bytes && M >= 4 * N && cudaGetDevice(&cur_dev) == cudaSuccess &&
-                cur_dev == w.device;
-    if (const char* e = getenv("KRS_TC_B_LO_TMA")) want = want && atoi(e) != 0;
+    if (cudaGetDevice(&cur_dev) != cudaSuccess) cur_dev = -1;
+    Workspace w = get_ws(cur_dev);
+    const bool want = env.b_lo_tma != 0 && w.ptr != nullptr && b_plane <= w.bytes && M >= 4 * N && cur_dev == w.device;
     if (want) {
       split_lo_kernel<<<(unsigned)imin<int64_t>(2 * sm_count(), ceil_div<int64_t>((int64_t)(b_plane / 16), 256)), 256, 0, stream>>>(
           reinterpret_cast<const float4*>(B), reinterpret_cast<float4*>(w.ptr), (int64_t)(b_plane / 16));
@@ -857,7 +878,7 @@ int gemm_tc(const float* A, int64_t lda, bool transA, const float* B, int64_t ld
   CUtensorMap ma, mb, mblo;
   bool ok;
   g.a_3d = g.b_3d = 0;
-  const bool allow3d = getenv("KRS_TC_NO_3D") == nullptr;
+  const bool allow3d = env.allow3d != 0;
   if (!g.a_mn_major) ok = make_map(&ma, A, M, K, lda, BK, BM, CU_TENSOR_MAP_SWIZZLE_64B);        // [M][K]
   else {
     ok = allow3d && make_map_3d(&ma, A, K, M, lda, BM / 32, (CUtensorMapSwizzle)a_mn_swz);
@@ -889,16 +910,23 @@ int gemm_tc(const float* A, int64_t lda, bool transA, const float* B, int64_t ld
   g.stages = (int)imin<int64_t>(MAX_STAGES, (int64_t)(budget / stage_bytes));
   if (g.stages < 3) return KRS_EUNSUPPORTED;
   const size_t smem = 1024 + g.stages * stage_bytes + EPI_SMEM_BYTES + 512;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    for (int v = 0; v < 2 && attr_err == cudaSuccess; ++v)
-      for (int k = 0; k < TK_COUNT && attr_err == cudaSuccess; ++k)
-        for (int a = 0; a < TA_COUNT && attr_err == cudaSuccess; ++a)
-          if (kernel_table(v + 1, k, a))
-            attr_err = cudaFuncSetAttribute(kernel_table(v + 1, k, a), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  });
-  KRS_CUDA(attr_err);
+  // the dynamic shared memory opt-in is a PER-DEVICE function attribute: once per device, not once per process
+  static std::once_flag once[MAX_DEVICES];
+  static cudaError_t attr_err[MAX_DEVICES];
+  {
+    int dev = 0;
+    KRS_CUDA(cudaGetDevice(&dev));
+    KRS_REQUIRE(dev >= 0 && dev < MAX_DEVICES, "gemm_tc: device index %d out of range", dev);
+    std::call_once(once[dev], [dev] {
+      attr_err[dev] = cudaSuccess;
+      for (int v = 0; v < 2 && attr_err[dev] == cudaSuccess; ++v)
+        for (int k = 0; k < TK_COUNT && attr_err[dev] == cudaSuccess; ++k)
+          for (int a = 0; a < TA_COUNT && attr_err[dev] == cudaSuccess; ++a)
+            if (kernel_table(v + 1, k, a))
+              attr_err[dev] = cudaFuncSetAttribute(kernel_table(v + 1, k, a), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    });
+    KRS_CUDA(attr_err[dev]);
+  }
   const int64_t total_tiles = (int64_t)g.tiles_m * g.tiles_n * g.splits;
   const unsigned grid = (unsigned)imax<int64_t>(1, imin<int64_t>(total_tiles, sm_count()));
   int kind;
@@ -936,7 +964,12 @@ extern "C" int krs_gemm_set_workspace(void* dev_buf, size_t bytes) {
     }
     dev = at.device;
   }
-  { std::lock_guard<std::mutex> l(krs::g_ws_mu); krs::g_ws_val = krs::Workspace{dev_buf, dev_buf ? bytes : 0, dev}; }
+  if (dev_buf == nullptr && cudaGetDevice(&dev) != cudaSuccess) dev = -1;     // NULL unregisters the current device's buffer
+  if (dev < 0 || dev >= krs::MAX_DEVICES) {
+    krs::set_error("krs_gemm_set_workspace: device index %d out of range", dev);
+    return KRS_EINVAL;
+  }
+  { std::lock_guard<std::mutex> l(krs::g_ws_mu); krs::g_ws_val[dev] = krs::Workspace{dev_buf, dev_buf ? bytes : 0, dev_buf ? dev : -1}; }
   return KRS_OK;
 }
 extern "C" long long krs_gemm_split_launch_count(void) { return krs::g_split_launches.load(); }

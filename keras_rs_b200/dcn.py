@@ -54,6 +54,8 @@ class DCN(torch.nn.Module):
                          kernel_initializer=initializers.GlorotUniform(seed=seed + 1 + i), device=device,
                          name=f"cross_{i}")
             for i in range(self.L)])
+        if dense_activation not in (None, "linear", "relu", "sigmoid", "tanh"):
+            raise ValueError(f"DCN's fused step supports dense_activation in linear / relu / sigmoid / tanh, got {dense_activation!r}")
         units = list(dense_units) + [1]
         acts = [dense_activation] * len(dense_units) + [None]      # examples/dcn.py:445 uses relu
         self.mlp = torch.nn.ModuleList([
@@ -67,6 +69,7 @@ class DCN(torch.nn.Module):
             d.build((None, k))
             k = d.units
         self._flatten_dense()
+        ops.ensure_gemm_workspace()            # per-device scratch of the tcgen05 engines, registered on first use
         self._bufs = {}
         self._plan = None
         self._plan_key = None

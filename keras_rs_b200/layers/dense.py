@@ -35,6 +35,11 @@ class Dense(Layer):
         self.use_bias = use_bias
         self.activation = activation
         self._act_id, self._act_fn, self._act_name = resolve_activation(activation)
+        if self._act_id == L.ACT["swish"]:
+            # the Dense backward keeps only y = act(z), from which swish'(z) cannot be recovered (krs_dense_bwd rejects it):
+            # swish / silu therefore runs as linear GEMM + the activation applied (and differentiated) on the pre-activation,
+            # exactly like a user callable.  FeatureCross keeps z and runs swish inside its epilogue.
+            self._act_id, self._act_fn = 0, torch.nn.functional.silu
         self.kernel_initializer = initializers.get(kernel_initializer)
         self.bias_initializer = initializers.get(bias_initializer)
         self.kernel_regularizer = kernel_regularizer

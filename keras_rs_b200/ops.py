@@ -23,21 +23,24 @@ _GEMM_WS: dict[int, torch.Tensor] = {}    # device index -> scratch registered w
 
 def ensure_gemm_workspace(nbytes: int = 32 << 20) -> None:
     """Registers a caller-owned scratch buffer for the tcgen05 engines (precomputed low-order TF32 plane of small B
-    operands, include/krs_b200.h krs_gemm_set_workspace).  One buffer per process/device, allocated once."""
-    if not torch.cuda.is_available():
+    operands, include/krs_b200.h krs_gemm_set_workspace) for the CURRENT device, once.  Called lazily where weights are
+    created / GEMMs are issued — never at import time (importing the package must not create a CUDA context, and a rank
+    that calls torch.cuda.set_device after the import must get its buffer on its own GPU).  The library keeps one
+    registration per device; GEMMs that use it must be issued on one stream at a time per device."""
+    if not torch.cuda.is_available() or lib.krs_get_gemm_engine() == 0:
         return
     dev = torch.cuda.current_device()
     if dev not in _GEMM_WS:
         _GEMM_WS[dev] = torch.empty(nbytes, dtype=torch.uint8, device=f"cuda:{dev}")
-    check(lib.krs_gemm_set_workspace(_GEMM_WS[dev].data_ptr(), _GEMM_WS[dev].numel()))
+        check(lib.krs_gemm_set_workspace(_GEMM_WS[dev].data_ptr(), _GEMM_WS[dev].numel()))
 
 
 def set_gemm_engine(name: str) -> None:
     """'ffma' (exact fp32 FMA products), 'tcgen05' (tensor pipe, 3xTF32 split, operands from shared memory) or
-    'tcgen05_ts' (same, A operand kept in tensor memory)."""
+    'tcgen05_ts' (same, A operand kept in tensor memory).  Process-wide switch; touches no CUDA state."""
     check(lib.krs_set_gemm_engine({"ffma": 0, "tcgen05": 1, "tcgen05_ts": 2}[name]))
-    if name != "ffma":
-        ensure_gemm_workspace()
+    if torch.cuda.is_available() and torch.cuda.is_initialized():
+        ensure_gemm_workspace()            # switching engines at run time: the current device gets its scratch now
 
 
 def get_gemm_engine() -> str:
@@ -249,6 +252,7 @@ class _CrossCombineFn(torch.autograd.Function):
 
 
 def feature_cross(x0, x, U, V, b, diag_scale, act: int, same_input: bool):
+    ensure_gemm_workspace()
     return _CrossFn.apply(x0, x, U, V, b, diag_scale or 0.0, act, same_input)
 
 
@@ -284,6 +288,7 @@ class _DenseFn(torch.autograd.Function):
 
 
 def dense(x, W, b, act: int):
+    ensure_gemm_workspace()
     return _DenseFn.apply(x, W, b, act)
 
 

@@ -25,16 +25,28 @@ def test_c4_full_size_topk_properties():
     # no candidate twice in a row of results
     srt = torch.sort(i, dim=1).values
     assert bool((srt[:, 1:] != srt[:, :-1]).all())
-    # every returned index carries its returned score (float64 recomputation, 512 sampled queries)
+    # every returned index carries its returned score (float64 recomputation, 512 sampled queries) at the reference
+    # test's own bar (brute_force_retrieval_test.py:59-64: scores 1e-4, indices exact)
     rows = torch.randperm(nq, device="cuda", generator=g)[:512]
     cand = C[i[rows].long()].double()                                        # (512, k, d)
     re = torch.einsum("qkd,qd->qk", cand, Q[rows].double())
-    assert float((re - s[rows].double()).abs().max()) <= 1e-3
-    # exact top-k of 8 queries in float64
-    ref = Q[:8].double() @ C.double().T
-    rs, _ = torch.topk(ref, k, dim=1)
-    assert bool(torch.allclose(s[:8].double(), rs, atol=1e-3))
-    assert float((torch.gather(ref, 1, i[:8].long()) - rs).abs().max()) < 1e-3
+    assert float((re - s[rows].double()).abs().max()) <= 1e-4
+    # exact float64 top-k of 256 sampled queries: scores within 1e-4, indices EXACTLY equal wherever the reference order is
+    # not a near-tie (neighbouring reference scores further apart than 2e-4; fp32-level scores cannot order closer pairs)
+    Cd = C.double()
+    checked = 0
+    for c0 in range(0, 256, 64):
+        qr = rows[c0:c0 + 64]
+        ref = Q[qr].double() @ Cd.T                                          # (64, 1e7) float64
+        rs, ri = torch.topk(ref, k + 1, dim=1)
+        assert float((s[qr].double() - rs[:, :k]).abs().max()) <= 1e-4
+        gap_prev = torch.cat([torch.full((64, 1), 1.0, device="cuda", dtype=torch.float64), rs[:, :k - 1] - rs[:, 1:k]], dim=1)
+        gap_next = rs[:, :k] - rs[:, 1:k + 1]
+        clear = (gap_prev > 2e-4) & (gap_next > 2e-4)
+        assert bool((i[qr].long()[clear] == ri[:, :k][clear]).all()), "top-k indices differ from the exact float64 ranking"
+        checked += int(clear.sum())
+        del ref
+    assert checked > 0.95 * 256 * k                                          # near-ties are rare: almost every slot was checked
 
 
 def test_c3_full_size_dot_interaction_properties():
