@@ -67,14 +67,16 @@ def prefetch(batches: Iterable[Sequence[torch.Tensor]], depth: int = 2, device: 
         else:
             break
     prev = None
-    while issued:
-        cur = issued.pop(0)
+    while True:
         main = torch.cuda.current_stream(dev)
         if prev is not None:                                    # everything enqueued on the batch just consumed ...
             prev.free = torch.cuda.Event()
             prev.free.record(main)                              # ... precedes the reuse of its slot
             if issue(prev):
                 issued.append(prev)
+        if not issued:
+            return
+        cur = issued.pop(0)
         main.wait_event(cur.ready)
         yield tuple(cur.dev)
         prev = cur
