@@ -183,6 +183,27 @@ int krs_topk(const float* Q, const float* C, const int32_t* cand_ids, float* top
              int32_t* top_ids, int64_t nq, int64_t nc, int d, int k, void* workspace,
              size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------ row-wise selection / masking (retrieval training)
+ * krs_row_topk: exact top-k of every row of x (rows, n), ld elements between rows, n <= 16384; values descending, ties ->
+ * lowest index first.  boost (nullable): the ordering key is x + boost * boost_scale while out_vals stay the unboosted
+ * x — HardNegativeMining (hard_negative_mining.py:43-94: top-(num_hard_negatives + 1) of logits + labels * MAX_FLOAT,
+ * then take_along_axis of logits and of labels = gather2 -> out_gather2).  Also merges the per-shard result lists of the
+ * candidate-sharded BruteForceRetrieval (multi-GPU caller: examples/data_parallel_retrieval.py:145-165). */
+int krs_row_topk(const float* x, int64_t rows, int n, int64_t ld, const float* boost, int64_t boost_ld, float boost_scale,
+                 int k, float* out_vals, int32_t* out_idx, const float* gather2, int64_t gather2_ld, float* out_gather2,
+                 void* stream);
+/* Backward of a row selection: dst (rows, n) = 0, dst[r, idx[r, j]] = g[r, j]. */
+int krs_row_scatter(const float* g, const int32_t* idx, int64_t rows, int k, int n, float* dst, void* stream);
+/* RemoveAccidentalHits.call (remove_accidental_hits.py:84-97), literally: positive index = argmax(labels[r]), positive
+ * id = take(FLATTENED candidate_ids, positive index), out = logits + ((ids == positive id) - labels) * smallest.
+ * candidate_ids: int32 / int64, one row of n ids shared by every row (ids_per_row = 0) or (rows, n) (ids_per_row = 1). */
+int krs_remove_accidental_hits(const float* logits, const float* labels, const void* candidate_ids, int ids_i64,
+                               int ids_per_row, int64_t rows, int n, float smallest, float* out, void* stream);
+/* SamplingProbabilityCorrection.call (sampling_probability_correction.py:39-58): out = logits - log(clip(p, eps, 1)),
+ * probs broadcast with period probs_period over the flattened logits. */
+int krs_sampling_prob_correction(const float* logits, const float* probs, int64_t total, int64_t probs_period, float eps,
+                                 float* out, void* stream);
+
 /* ------------------------------------------------------------------ losses
  * keras.losses.MeanSquaredError / BinaryCrossentropy(from_logits=False) on (B,1) predictions
  * (examples/dcn.py:128, examples/ml_perf/main.py:201-210): loss scalar (mean over B) and

@@ -79,6 +79,10 @@ _sig("krs_set_topk_engine", C.c_int, i32)
 _sig("krs_topk_tc_launch_count", C.c_longlong)
 _sig("krs_topk", C.c_int, c_f32p, c_f32p, C.c_void_p, c_f32p, C.c_void_p, i64, i64, i32, i32,
      C.c_void_p, C.c_size_t, C.c_void_p)
+_sig("krs_row_topk", C.c_int, c_f32p, i64, i32, i64, c_f32p, i64, C.c_float, i32, c_f32p, C.c_void_p, c_f32p, i64, c_f32p, C.c_void_p)
+_sig("krs_row_scatter", C.c_int, c_f32p, C.c_void_p, i64, i32, i32, c_f32p, C.c_void_p)
+_sig("krs_remove_accidental_hits", C.c_int, c_f32p, c_f32p, C.c_void_p, i32, i32, i64, i32, C.c_float, c_f32p, C.c_void_p)
+_sig("krs_sampling_prob_correction", C.c_int, c_f32p, c_f32p, i64, i64, C.c_float, c_f32p, C.c_void_p)
 _sig("krs_loss_fwd_bwd", C.c_int, c_f32p, c_f32p, c_f32p, c_f32p, i64, i32, i64, C.c_void_p)
 _sig("krs_adamw", C.c_int, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p, i64, i32, C.c_float,
      C.c_float, C.c_float, C.c_float, C.c_float, i64, c_f32p, C.c_void_p)
@@ -125,7 +129,8 @@ EXPORTED = [
     "krs_version", "krs_last_error", "krs_device_sm_count", "krs_set_gemm_engine",
     "krs_get_gemm_engine", "krs_gemm_tc_launch_count", "krs_gemm_tc_set_trace", "krs_gemm_set_workspace", "krs_gemm_split_launch_count", "krs_gather_fwd", "krs_gather_bwd", "krs_cross_fwd", "krs_cross_bwd",
     "krs_cross_combine_fwd", "krs_cross_combine_bwd", "krs_dense_fwd", "krs_dense_bwd", "krs_sgemm",
-    "krs_dot_fwd", "krs_dot_bwd", "krs_topk_workspace_bytes", "krs_topk", "krs_set_topk_engine", "krs_topk_tc_launch_count", "krs_loss_fwd_bwd",
+    "krs_dot_fwd", "krs_dot_bwd", "krs_topk_workspace_bytes", "krs_topk", "krs_set_topk_engine", "krs_topk_tc_launch_count", "krs_row_topk", "krs_row_scatter",
+    "krs_remove_accidental_hits", "krs_sampling_prob_correction", "krs_loss_fwd_bwd",
     "krs_adamw", "krs_adamw_cold", "krs_adam_hyper_advance", "krs_sgd_adagrad", "krs_mod_route",
     "krs_xchg_route_workspace_bytes", "krs_xchg_route", "krs_xchg_barrier", "krs_xchg_gather_push", "krs_slot_scan_blocks",
     "krs_slot_scan", "krs_xchg_grad_pull", "krs_rows_apply", "krs_adamw_compact", "krs_ipc_alloc", "krs_ipc_open",

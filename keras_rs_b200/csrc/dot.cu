@@ -175,7 +175,22 @@ __global__ void __launch_bounds__(128) dot_bwd_mma_kernel(const __grid_constant_
         split_tf32(Sw[16 * mt + g][8 * kt + t + 4], ah[mt][kt][2], al[mt][kt][2]);
         split_tf32(Sw[16 * mt + g + 8][8 * kt + t + 4], ah[mt][kt][3], al[mt][kt][3]);
       }
+    // B operands (feature rows) of one 32-wide chunk: 2 x float4 per k-tile, all 8 loads issued together, and the NEXT
+    // chunk's loads are in flight while this one feeds the tensor core.  (Loading f0 / f1 inside the k-tile loop, right
+    // before their split, exposed one global-load latency per k-tile — 16 per sample — and held the backward at ~21 % of
+    // the HBM roofline; the mma asm is volatile, so the compiler cannot hoist the loads itself.)
+    float4 fc[4][2], fn[4][2];
+    auto load_chunk = [&](float4 (&dst)[4][2], int e0) {
+#pragma unroll
+      for (int kt = 0; kt < 4; ++kt) {
+        const int r0 = 8 * kt + t, r1 = 8 * kt + t + 4;
+        dst[kt][0] = r0 < N ? ldg_nc_f4(p.feat[r0] + b * p.stride[r0] + e0 + 4 * g) : make_float4(0.f, 0.f, 0.f, 0.f);
+        dst[kt][1] = r1 < N ? ldg_nc_f4(p.feat[r1] + b * p.stride[r1] + e0 + 4 * g) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    load_chunk(fc, 0);
     for (int e0 = 0; e0 < E; e0 += 32) {
+      if (e0 + 32 < E) load_chunk(fn, e0 + 32);
       float acc[2][4][4];
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt)
@@ -186,9 +201,7 @@ __global__ void __launch_bounds__(128) dot_bwd_mma_kernel(const __grid_constant_
 #pragma unroll
       for (int kt = 0; kt < 4; ++kt) {
         // B(k = feature, n): column n=g of n-tile nt maps to e = e0 + 4g + nt  => one float4 per row
-        const int r0 = 8 * kt + t, r1 = 8 * kt + t + 4;
-        float4 f0 = r0 < N ? ldg_nc_f4(p.feat[r0] + b * p.stride[r0] + e0 + 4 * g) : make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 f1 = r1 < N ? ldg_nc_f4(p.feat[r1] + b * p.stride[r1] + e0 + 4 * g) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 f0 = fc[kt][0], f1 = fc[kt][1];
         const float b0v[4] = {f0.x, f0.y, f0.z, f0.w};
         const float b1v[4] = {f1.x, f1.y, f1.z, f1.w};
 #pragma unroll
@@ -218,6 +231,8 @@ __global__ void __launch_bounds__(128) dot_bwd_mma_kernel(const __grid_constant_
                                                             acc[mt][2][2 * half + 1], acc[mt][3][2 * half + 1]);
           }
         }
+#pragma unroll
+      for (int kt = 0; kt < 4; ++kt) { fc[kt][0] = fn[kt][0]; fc[kt][1] = fn[kt][1]; }
     }
   }
 }

@@ -243,6 +243,126 @@ __global__ void __launch_bounds__(256) gather_bulk_kernel(const __grid_constant_
   if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+// ------------------------------------------------------------------ forward, multi-hot "sample" path
+// One lane group (lpr lanes, one float4 column each) per SAMPLE.  The lookups of all the sample's features are walked as ONE
+// flattened sequence l = 0 .. sum(H)-1 with HU row loads in flight at any time, whatever the hotness of the individual
+// feature: in the ml_perf feature list (examples/ml_perf/configs/v6e_8.py:15-172) 14 of the 26 features are one-hot and one
+// has 100 ids, and a group-per-(sample, feature) kernel keeps a single 512-byte load in flight for most of its items
+// (measured 2.06 TB/s = 31 % of the HBM roofline).  Per feature the sum still runs h = 0 .. H-1 in order without FMA
+// contraction, so results are bit-identical to gather_generic_kernel and to the oracle (embed_reduce.py:253-274).
+// Requirements (host-checked): every dim a multiple of 4 and <= 128, 16-byte aligned tables / output, sum(H) <= SAMPLE_MAXL.
+constexpr int SAMPLE_MAXL = 2048;
+struct FeatSample {
+  const float* table;
+  const void* ids;
+  const float* weights;      // nullptr unless honoured (embed_reduce.py:224)
+  const float* const* shards;
+  long long vocab, stride;
+  int nshards, i64, nchunk, hot, out_off, div_kind;   // div_kind: 0 none, 1 mean, 2 sqrtn
+};
+
+template <int HU>
+__global__ void __launch_bounds__(256) gather_sample_kernel(const __grid_constant__ GatherParams p, int lpr, int total_hot) {
+  __shared__ FeatSample sf[MAXF];
+  __shared__ unsigned char lk_feat[SAMPLE_MAXL];
+  __shared__ int first[MAXF + 1];
+  for (int i = threadIdx.x; i < p.F; i += blockDim.x) {
+    const krs_feature_t& f = p.f[i];
+    FeatSample t;
+    t.table = f.table;
+    t.ids = f.ids;
+    t.weights = (f.weights != nullptr && (f.reduce || f.combiner == KRS_COMBINER_SUM)) ? f.weights : nullptr;
+    t.shards = f.shard_tables;
+    t.vocab = f.vocab;
+    t.stride = f.ids_stride;
+    t.nshards = f.num_shards;
+    t.i64 = f.ids_i64;
+    t.nchunk = f.dim / 4;
+    t.hot = f.hotness;
+    t.out_off = f.out_offset;
+    t.div_kind = (f.reduce && f.combiner != KRS_COMBINER_SUM) ? (f.combiner == KRS_COMBINER_MEAN ? 1 : 2) : 0;
+    sf[i] = t;
+  }
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int i = 0; i < p.F; ++i) { first[i] = run; run += p.f[i].hotness; }
+    first[p.F] = run;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < p.F; i += blockDim.x)
+    for (int l = first[i]; l < first[i + 1]; ++l) lk_feat[l] = (unsigned char)i;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % lpr, gsub = lane / lpr;
+  const int groups = 32 / lpr;
+  const int64_t ngroups = (((int64_t)gridDim.x * blockDim.x) >> 5) * groups;
+  for (int64_t b = ((((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * groups) + gsub; b < p.B; b += ngroups) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float dsum = 0.f;
+    for (int l0 = 0; l0 < total_hot; l0 += HU) {
+      const float* src[HU];
+      float w[HU];
+      float4 v[HU];
+      int fe[HU];
+#pragma unroll
+      for (int u = 0; u < HU; ++u) {
+        src[u] = nullptr;
+        w[u] = 1.f;
+        fe[u] = -1;
+        const int l = l0 + u;
+        if (l < total_hot) {
+          const int f = lk_feat[l];
+          const FeatSample& ft = sf[f];
+          fe[u] = f;
+          const int64_t idx = b * ft.stride + (l - first[f]);
+          const int64_t id = resolve_id(ft.i64 ? load_id<int64_t>(ft.ids, idx) : load_id<int32_t>(ft.ids, idx), ft.vocab);
+          if (ft.weights) w[u] = ft.weights[idx];
+          if (id < 0) src[u] = nan_row();
+          else if (sub < ft.nchunk) {
+            const int dim = ft.nchunk * 4;
+            src[u] = (ft.nshards > 1 ? ft.shards[(int)(id % ft.nshards)] + (id / ft.nshards) * (int64_t)dim : ft.table + id * (int64_t)dim) + sub * 4;
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < HU; ++u) {
+        if (src[u] == nan_row()) v[u] = nan4();        // no such row: NaN (jnp.take "fill") poisons the reduced sample
+        else if (src[u] != nullptr) v[u] = ldg_nc_f4(src[u]);
+        else v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < HU; ++u) {
+        if (fe[u] < 0) continue;
+        const FeatSample& ft = sf[fe[u]];
+        const int h = l0 + u - first[fe[u]];
+        if (h == 0) {
+          acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          dsum = 0.f;
+        }
+        // x = x * w ; sum over axis -2 in order h = 0..H-1 (no FMA contraction: embed_reduce.py:253,261)
+        if (ft.hot == 1) {
+          acc.x = __fmul_rn(v[u].x, w[u]); acc.y = __fmul_rn(v[u].y, w[u]); acc.z = __fmul_rn(v[u].z, w[u]); acc.w = __fmul_rn(v[u].w, w[u]);
+        } else {
+          acc.x = __fadd_rn(acc.x, __fmul_rn(v[u].x, w[u])); acc.y = __fadd_rn(acc.y, __fmul_rn(v[u].y, w[u]));
+          acc.z = __fadd_rn(acc.z, __fmul_rn(v[u].z, w[u])); acc.w = __fadd_rn(acc.w, __fmul_rn(v[u].w, w[u]));
+        }
+        if (ft.div_kind) dsum = ft.div_kind == 1 ? __fadd_rn(dsum, w[u]) : __fadd_rn(dsum, __fmul_rn(w[u], w[u]));
+        if (h == ft.hot - 1 && sub < ft.nchunk) {
+          float4 r = acc;
+          if (ft.div_kind) {
+            const float div = ft.div_kind == 1 ? dsum : sqrtf(dsum);
+            r.x = (div != 0.f) ? __fdiv_rn(r.x, div) : 0.f;   // divide_no_nan
+            r.y = (div != 0.f) ? __fdiv_rn(r.y, div) : 0.f;
+            r.z = (div != 0.f) ? __fdiv_rn(r.z, div) : 0.f;
+            r.w = (div != 0.f) ? __fdiv_rn(r.w, div) : 0.f;
+          }
+          stg_cs_f4(p.out + b * p.out_ld + ft.out_off + sub * 4, r);
+        }
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------ forward, generic path
 // One lane group of `lpr` lanes per (b,f) item; element unit = float4 (VEC) or float.
 template <bool VEC>
@@ -409,7 +529,7 @@ __global__ void __launch_bounds__(256) scatter_fast_kernel(const __grid_constant
 
 
 // Generic: warp per (b,f) item, loops over hotness; coefficient = w / divisor.
-__global__ void __launch_bounds__(256) scatter_generic_kernel(const __grid_constant__ GatherParams p) {
+__global__ void __launch_bounds__(256) scatter_generic_kernel(const __grid_constant__ GatherParams p, bool vec) {
   const int lane = threadIdx.x & 31;
   const int64_t items = p.B * p.F;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -449,7 +569,14 @@ __global__ void __launch_bounds__(256) scatter_generic_kernel(const __grid_const
           atomicOr(ft.touched + (id >> 5), 1u << (id & 31));
         }
       }
-      for (int c = lane; c < E; c += 32) atomicAdd(drow + c, coef * g[c]);
+      if (vec) {                                         // one 16-byte reduction per lane instead of four scalar ones
+        for (int c = lane * 4; c < E; c += 128) {
+          const float4 gv = *reinterpret_cast<const float4*>(g + c);
+          atomicAdd(reinterpret_cast<float4*>(drow + c), make_float4(coef * gv.x, coef * gv.y, coef * gv.z, coef * gv.w));
+        }
+      } else {
+        for (int c = lane; c < E; c += 32) atomicAdd(drow + c, coef * g[c]);
+      }
     }
   }
 }
@@ -582,6 +709,16 @@ extern "C" int krs_gather_fwd(const krs_feature_t* features, int F, int64_t B, f
   const int chunks = vec ? maxE / 4 : maxE;
   int lpr = 1;
   while (lpr < chunks && lpr < 32) lpr <<= 1;
+  int64_t total_hot = 0;
+  for (int i = 0; i < F; ++i) total_hot += p.f[i].hotness;
+  if (vec && variant != 3 && maxE <= 128 && total_hot <= SAMPLE_MAXL && F <= 255) {
+    // flattened per-sample walk: a constant number of row loads in flight whatever the per-feature hotness
+    const int64_t warps_needed = ceil_div<int64_t>(B, 32 / lpr);
+    const unsigned grid = (unsigned)krs::imax<int64_t>(1, krs::imin<int64_t>(ceil_div<int64_t>(warps_needed, 8), (int64_t)sm_count() * 64));
+    gather_sample_kernel<8><<<grid, 256, 0, s>>>(p, lpr, (int)total_hot);
+    KRS_LAUNCH_CHECK();
+    return KRS_OK;
+  }
   const int64_t items = B * F;
   const int64_t warps_needed = ceil_div<int64_t>(items, 32 / lpr);
   const unsigned grid = (unsigned)krs::imax<int64_t>(1, krs::imin<int64_t>(ceil_div<int64_t>(warps_needed, 8), (int64_t)sm_count() * 32));
@@ -634,7 +771,12 @@ extern "C" int krs_gather_bwd(const krs_feature_t* features, int F, int64_t B, c
   } else {
     const int64_t items = B * F;
     const unsigned grid = (unsigned)krs::imax<int64_t>(1, krs::imin<int64_t>(ceil_div<int64_t>(items, 8), (int64_t)sm_count() * 32));
-    scatter_generic_kernel<<<grid, 256, 0, s>>>(p);
+    bool vec = aligned16(gout) && (gout_ld % 4 == 0);
+    for (int i = 0; i < F && vec; ++i) {
+      const krs_feature_t& f = p.f[i];
+      if (f.dim % 4 != 0 || f.out_offset % 4 != 0 || (f.num_shards <= 1 && !aligned16(f.grad))) vec = false;
+    }
+    scatter_generic_kernel<<<grid, 256, 0, s>>>(p, vec);
   }
   KRS_LAUNCH_CHECK();
   return KRS_OK;
