@@ -191,7 +191,8 @@ int krs_topk(const float* Q, const float* C, const int32_t* cand_ids, float* top
  * candidate-sharded BruteForceRetrieval (multi-GPU caller: examples/data_parallel_retrieval.py:145-165). */
 int krs_row_topk(const float* x, int64_t rows, int n, int64_t ld, const float* boost, int64_t boost_ld, float boost_scale,
                  int k, float* out_vals, int32_t* out_idx, const float* gather2, int64_t gather2_ld, float* out_gather2,
-                 void* stream);
+                 const int32_t* gather_i32 /* nullable int32 payload, e.g. candidate ids */, int64_t gather_i32_ld,
+                 int32_t* out_gather_i32, void* stream);
 /* Backward of a row selection: dst (rows, n) = 0, dst[r, idx[r, j]] = g[r, j]. */
 int krs_row_scatter(const float* g, const int32_t* idx, int64_t rows, int k, int n, float* dst, void* stream);
 /* RemoveAccidentalHits.call (remove_accidental_hits.py:84-97), literally: positive index = argmax(labels[r]), positive

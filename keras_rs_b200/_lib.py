@@ -79,7 +79,8 @@ _sig("krs_set_topk_engine", C.c_int, i32)
 _sig("krs_topk_tc_launch_count", C.c_longlong)
 _sig("krs_topk", C.c_int, c_f32p, c_f32p, C.c_void_p, c_f32p, C.c_void_p, i64, i64, i32, i32,
      C.c_void_p, C.c_size_t, C.c_void_p)
-_sig("krs_row_topk", C.c_int, c_f32p, i64, i32, i64, c_f32p, i64, C.c_float, i32, c_f32p, C.c_void_p, c_f32p, i64, c_f32p, C.c_void_p)
+_sig("krs_row_topk", C.c_int, c_f32p, i64, i32, i64, c_f32p, i64, C.c_float, i32, c_f32p, C.c_void_p, c_f32p, i64, c_f32p,
+     C.c_void_p, i64, C.c_void_p, C.c_void_p)
 _sig("krs_row_scatter", C.c_int, c_f32p, C.c_void_p, i64, i32, i32, c_f32p, C.c_void_p)
 _sig("krs_remove_accidental_hits", C.c_int, c_f32p, c_f32p, C.c_void_p, i32, i32, i64, i32, C.c_float, c_f32p, C.c_void_p)
 _sig("krs_sampling_prob_correction", C.c_int, c_f32p, c_f32p, i64, i64, C.c_float, c_f32p, C.c_void_p)

@@ -29,7 +29,8 @@ __global__ void __launch_bounds__(512) row_topk_kernel(const float* __restrict__
                                                        int64_t ld, int64_t boost_ld, int n, int npad, int k,
                                                        float* __restrict__ out_vals, int32_t* __restrict__ out_idx,
                                                        const float* __restrict__ gather2, int64_t gather2_ld,
-                                                       float* __restrict__ out_gather2) {
+                                                       float* __restrict__ out_gather2, const int32_t* __restrict__ gather_i,
+                                                       int64_t gather_i_ld, int32_t* __restrict__ out_gather_i) {
   extern __shared__ unsigned long long keys[];
   const int64_t r = blockIdx.x;
   const float* row = x + r * ld;
@@ -62,6 +63,7 @@ __global__ void __launch_bounds__(512) row_topk_kernel(const float* __restrict__
     out_idx[r * k + j] = idx;
     out_vals[r * k + j] = row[idx];                        // the unboosted value
     if (gather2) out_gather2[r * k + j] = gather2[r * gather2_ld + idx];
+    if (gather_i) out_gather_i[r * k + j] = gather_i[r * gather_i_ld + idx];
   }
 }
 
@@ -130,11 +132,12 @@ using namespace krs;
 
 extern "C" int krs_row_topk(const float* x, int64_t rows, int n, int64_t ld, const float* boost, int64_t boost_ld, float boost_scale,
                             int k, float* out_vals, int32_t* out_idx, const float* gather2, int64_t gather2_ld, float* out_gather2,
-                            void* stream) {
+                            const int32_t* gather_i32, int64_t gather_i32_ld, int32_t* out_gather_i32, void* stream) {
   KRS_REQUIRE(x && out_vals && out_idx, "krs_row_topk: null argument");
   KRS_REQUIRE(rows >= 0 && n >= 1 && n <= ROW_MAX_N && ld >= n, "krs_row_topk: need 1 <= n <= %d and ld >= n", ROW_MAX_N);
   KRS_REQUIRE(k >= 1 && k <= n, "krs_row_topk: need 1 <= k <= n");
   KRS_REQUIRE((gather2 == nullptr) == (out_gather2 == nullptr), "krs_row_topk: gather2 and out_gather2 go together");
+  KRS_REQUIRE((gather_i32 == nullptr) == (out_gather_i32 == nullptr), "krs_row_topk: gather_i32 and out_gather_i32 go together");
   if (rows == 0) return KRS_OK;
   int npad = 2;
   while (npad < n) npad <<= 1;
@@ -142,7 +145,8 @@ extern "C" int krs_row_topk(const float* x, int64_t rows, int n, int64_t ld, con
   if (smem > 48 * 1024) KRS_CUDA(cudaFuncSetAttribute(row_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int threads = npad / 2 < 64 ? 64 : (npad / 2 > 512 ? 512 : npad / 2);
   row_topk_kernel<<<(unsigned)rows, threads, smem, as_stream(stream)>>>(x, boost, boost_scale, ld, boost_ld, n, npad, k, out_vals, out_idx,
-                                                                       gather2, gather2_ld, out_gather2);
+                                                                       gather2, gather2_ld, out_gather2, gather_i32, gather_i32_ld,
+                                                                       out_gather_i32);
   KRS_LAUNCH_CHECK();
   return KRS_OK;
 }

@@ -6,9 +6,9 @@ from .distributed_embedding import DistributedEmbedding, FeatureConfig, TableCon
 from .dot_interaction import DotInteraction
 from .embedding import EmbedReduce, Embedding
 from .feature_cross import FeatureCross
-from .retrieval import BruteForceRetrieval, Retrieval
+from .retrieval import BruteForceRetrieval, CandidateShardedRetrieval, Retrieval, merge_top_k
 from .retrieval_helpers import HardNegativeMining, RemoveAccidentalHits, SamplingProbabilityCorrection
 
 __all__ = ["Layer", "Dense", "Embedding", "EmbedReduce", "DistributedEmbedding", "TableConfig", "FeatureConfig",
-           "FeatureCross", "DotInteraction", "Retrieval", "BruteForceRetrieval", "HardNegativeMining", "RemoveAccidentalHits",
+           "FeatureCross", "DotInteraction", "Retrieval", "BruteForceRetrieval", "CandidateShardedRetrieval", "merge_top_k", "HardNegativeMining", "RemoveAccidentalHits",
            "SamplingProbabilityCorrection", "serialize", "deserialize"]

@@ -123,3 +123,60 @@ class BruteForceRetrieval(Retrieval):
     def compute_output_shape(self, input_shape):
         s = tuple(input_shape[:-1]) + (self.k,)
         return (s, s) if self.return_scores else s
+
+
+def merge_top_k(scores: torch.Tensor, ids: torch.Tensor, k: int):
+    """Exact top-k of the concatenated per-shard result lists: scores, ids (nq, m) -> (nq, k), scores descending, ties ->
+    lowest position first (csrc/rowops.cu krs_row_topk).  With shards that hold contiguous, increasing id ranges and lists
+    concatenated in shard order, position order IS id order, so the merged result equals the unsharded top-k."""
+    from .._lib import check, lib, ptr, stream
+    L.require_cuda(scores, "scores")
+    L.require_cuda(ids, "ids", dtype=torch.int32)
+    scores, ids = scores.contiguous(), ids.contiguous()
+    nq, m = scores.shape
+    out_s = torch.empty((nq, k), device=scores.device, dtype=torch.float32)
+    out_pos = torch.empty((nq, k), device=scores.device, dtype=torch.int32)
+    out_i = torch.empty((nq, k), device=scores.device, dtype=torch.int32)
+    check(lib.krs_row_topk(ptr(scores), nq, m, m, None, 0, 0.0, k, ptr(out_s), ptr(out_pos), None, 0, None, ptr(ids), m, ptr(out_i),
+                           stream()))
+    return out_s, out_i
+
+
+class CandidateShardedRetrieval(torch.nn.Module):
+    """BruteForceRetrieval over candidates split row-wise across the GPUs of one box (the multi-GPU caller in
+    the reference is examples/data_parallel_retrieval.py:145-165, which replicates the candidates — at C4 size, 1e7 x 64
+    floats, every GPU would stream the same 2.56 GB per query batch; sharded, each GPU streams 1/S of it).
+
+    Every rank holds the contiguous slice [first_id, first_id + n_local) of the candidate matrix and receives the SAME query
+    batch.  Per call: local exact top-k on the tensor-pipe scorer (csrc/topk.cu) with global candidate ids, all-gather of
+    the (nq, k) lists (NCCL: a real collective, S * nq * k * 8 bytes), one krs_row_topk merge.  `group=None` with
+    world_size 1 (or no process group) degenerates to the local search."""
+
+    def __init__(self, local_candidates: torch.Tensor, first_id: int, k: int = 10, candidate_ids: torch.Tensor | None = None,
+                 return_scores: bool = True, group=None):
+        super().__init__()
+        L.require_cuda(local_candidates, "local_candidates")
+        self.k, self.return_scores, self.group = int(k), return_scores, group
+        self.candidates = local_candidates.detach().contiguous()
+        n = self.candidates.shape[0]
+        if candidate_ids is None:
+            candidate_ids = torch.arange(first_id, first_id + n, device=self.candidates.device, dtype=torch.int32)
+        self.ids = candidate_ids.to(torch.int32).contiguous()
+
+    def local_top_k(self, q: torch.Tensor):
+        k = min(self.k, self.candidates.shape[0])
+        return ops.top_k_scores(q.detach().contiguous(), self.candidates, self.ids, k)
+
+    def forward(self, q: torch.Tensor):
+        import torch.distributed as dist
+        s, i = self.local_top_k(q)
+        world = dist.get_world_size(self.group) if (dist.is_available() and dist.is_initialized()) else 1
+        if world > 1:
+            if s.shape[1] != self.k:
+                raise ValueError("CandidateShardedRetrieval: every shard must hold at least k candidates")
+            gs = torch.empty((world,) + tuple(s.shape), device=s.device, dtype=s.dtype)
+            gi = torch.empty((world,) + tuple(i.shape), device=i.device, dtype=i.dtype)
+            dist.all_gather_into_tensor(gs, s, group=self.group)
+            dist.all_gather_into_tensor(gi, i, group=self.group)
+            s, i = merge_top_k(gs.permute(1, 0, 2).reshape(s.shape[0], -1), gi.permute(1, 0, 2).reshape(i.shape[0], -1), self.k)
+        return (s, i) if self.return_scores else i

@@ -1,10 +1,9 @@
 """HardNegativeMining, RemoveAccidentalHits, SamplingProbabilityCorrection — the two-tower TRAINING helpers of
-keras_rs.layers ("next": they feed the loss of the retrieval model, not the hot path
-gather -> cross -> dense this package accelerates).
-
-These are thin host-side mirrors with the reference's names, constructor arguments, call signatures, error messages and
-arithmetic, composed from torch tensor ops on whatever device the inputs live on; they launch no kernel of
-libkrs_b200.so.  Fusing them into the score epilogue of the tensor-pipe scorer (csrc/topk.cu) is the planned CUDA form.
+keras_rs.layers, with the reference's names, constructor arguments, call signatures, error
+messages and arithmetic, running on the row kernels of csrc/rowops.cu (krs_row_topk with a label boost, krs_row_scatter
+for its backward, krs_remove_accidental_hits, krs_sampling_prob_correction).  CUDA tensors only — like the rest of the
+package there is no CPU path.  Gradients flow to `logits` (row selection: scatter of the selected columns; the two additive
+corrections: identity); labels, ids and sampling probabilities receive none.
 
 References: hard_negative_mining.py:43-94, remove_accidental_hits.py:32-97,
 sampling_probability_correction.py:39-63 (all under keras_rs/src/layers/retrieval/)."""
@@ -15,6 +14,8 @@ from typing import Any
 import numpy as np
 import torch
 
+from .. import _lib as L
+from .._lib import check, lib, ptr, stream
 from .base import Layer, register
 
 # hard_negative_mining.py:9  (ml_dtypes.finfo("float32").max / 100.0)
@@ -29,6 +30,51 @@ def _shapes_compatible(a, b) -> bool:
     return len(a) == len(b) and all(int(x) == int(y) for x, y in zip(a, b))
 
 
+class _RowSelectFn(torch.autograd.Function):
+    """top-k columns of every row ordered by logits + labels * MAX_FLOAT; returns the selected logits and labels."""
+
+    @staticmethod
+    def forward(ctx, x, y, k):
+        rows, n = x.shape
+        out_l = torch.empty((rows, k), device=x.device, dtype=torch.float32)
+        out_y = torch.empty((rows, k), device=x.device, dtype=torch.float32)
+        idx = torch.empty((rows, k), device=x.device, dtype=torch.int32)
+        check(lib.krs_row_topk(ptr(x), rows, n, n, ptr(y), n, MAX_FLOAT, k, ptr(out_l), ptr(idx), ptr(y), n, ptr(out_y), None, 0, None,
+                               stream()))
+        ctx.save_for_backward(idx)
+        ctx.n = n
+        ctx.mark_non_differentiable(out_y)
+        return out_l, out_y
+
+    @staticmethod
+    def backward(ctx, g_l, g_y):
+        (idx,) = ctx.saved_tensors
+        rows, k = idx.shape
+        g = g_l.contiguous()
+        dx = torch.empty((rows, ctx.n), device=g.device, dtype=torch.float32)
+        check(lib.krs_row_scatter(ptr(g), ptr(idx), rows, k, ctx.n, ptr(dx), stream()))
+        return dx, None, None
+
+
+class _AdditiveFn(torch.autograd.Function):
+    """logits + (a correction that does not depend on the logits): identity gradient."""
+
+    @staticmethod
+    def forward(ctx, x, kind, aux, ids, per_row, scalar):
+        out = torch.empty_like(x)
+        if kind == "hits":
+            rows, n = x.shape
+            check(lib.krs_remove_accidental_hits(ptr(x), ptr(aux), ptr(ids), 1 if ids.dtype == torch.int64 else 0, per_row, rows, n,
+                                                 scalar, ptr(out), stream()))
+        else:
+            check(lib.krs_sampling_prob_correction(ptr(x), ptr(aux), x.numel(), max(aux.numel(), 1), scalar, ptr(out), stream()))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None, None, None, None, None
+
+
 @register("keras_rs.layers.HardNegativeMining")
 class HardNegativeMining(Layer):
     """Keeps, per row, the positive candidate and the `num_hard_negatives` highest-scoring negatives
@@ -41,11 +87,15 @@ class HardNegativeMining(Layer):
         self.built = True
 
     def call(self, logits: torch.Tensor, labels: torch.Tensor):
+        L.require_cuda(logits, "logits")
+        L.require_cuda(labels, "labels", dtype=None)
         num_logits = logits.shape[-1]
         num_sampled = min(self._num_hard_negatives + 1, num_logits)              # :70-75
-        boosted = logits + labels.to(logits.dtype) * MAX_FLOAT                   # :88
-        _, indices = torch.topk(boosted, k=num_sampled, dim=-1, largest=True, sorted=True)
-        return torch.take_along_dim(logits, indices, dim=-1), torch.take_along_dim(labels, indices, dim=-1)
+        lead = logits.shape[:-1]
+        x = logits.reshape(-1, num_logits).contiguous()
+        y = labels.reshape(-1, num_logits).to(torch.float32).contiguous()
+        out_logits, out_labels = _RowSelectFn.apply(x, y, num_sampled)           # :88-94
+        return out_logits.reshape(*lead, num_sampled), out_labels.reshape(*lead, num_sampled).to(labels.dtype)
 
     def compute_output_shape(self, logits_shape, labels_shape=None):
         out = tuple(logits_shape[:-1]) + (min(self._num_hard_negatives + 1, logits_shape[-1]),)
@@ -76,11 +126,21 @@ class RemoveAccidentalHits(Layer):
         if not _shapes_compatible(labels_shape[len(labels_shape) - ids_rank:] if ids_rank else (), ids_shape):
             raise ValueError("`candidate_ids` should have the same shape as the last dimensions of `labels`. Received: "
                              f"`candidate_ids.shape` = {ids_shape}, `labels.shape` = {labels_shape}.")
-        ids = candidate_ids.reshape((1,) * (len(labels_shape) - ids_rank) + ids_shape)       # :84-90
-        positive_indices = torch.argmax(labels, dim=-1, keepdim=True)                       # :91
-        positive_ids = candidate_ids.reshape(-1)[positive_indices]                          # :92-93 (flattened take)
-        duplicate = (positive_ids == ids).to(labels.dtype) - labels                         # :94-96
-        return logits + duplicate.to(logits.dtype) * SMALLEST_FLOAT                         # :97
+        L.require_cuda(logits, "logits")
+        L.require_cuda(labels, "labels", dtype=None)
+        L.require_cuda(candidate_ids, "candidate_ids", dtype=None)
+        n = logits_shape[-1] if logits_shape else 1
+        x = logits.reshape(-1, n).contiguous()
+        y = labels.reshape(-1, n).to(torch.float32).contiguous()
+        ids = candidate_ids if candidate_ids.dtype in (torch.int32, torch.int64) else candidate_ids.to(torch.int64)
+        # ids broadcast over the leading dims of labels (:84-90).  The kernel takes one shared row of ids or one row per
+        # logits row; anything in between is expanded.  The positive id is taken from the FLATTENED ids (:92-93).
+        if ids_rank <= 1:
+            ids2, per_row = ids.reshape(-1).contiguous(), 0
+        else:
+            ids2 = ids.reshape((1,) * (len(labels_shape) - ids_rank) + ids_shape).expand(labels_shape).reshape(-1, n).contiguous()
+            per_row = 1
+        return _AdditiveFn.apply(x, "hits", y, ids2, per_row, SMALLEST_FLOAT).reshape(logits_shape)
 
     def compute_output_shape(self, logits_shape, *unused):
         return tuple(logits_shape)
@@ -96,8 +156,13 @@ class SamplingProbabilityCorrection(Layer):
         self.built = True
 
     def call(self, logits: torch.Tensor, candidate_sampling_probability: torch.Tensor) -> torch.Tensor:
-        p = candidate_sampling_probability.to(logits.dtype)
-        return logits - torch.log(torch.clamp(p, self.epsilon, 1.0))
+        L.require_cuda(logits, "logits")
+        L.require_cuda(candidate_sampling_probability, "candidate_sampling_probability", dtype=None)
+        p = candidate_sampling_probability.to(torch.float32)
+        if p.dim() > logits.dim() or tuple(logits.shape[logits.dim() - p.dim():]) != tuple(p.shape):
+            p = p.expand(logits.shape)                                            # general numpy broadcasting, off the fast path
+        p = p.contiguous()
+        return _AdditiveFn.apply(logits.contiguous(), "prob", p, None, 0, float(self.epsilon))
 
     def compute_output_shape(self, logits_shape, *unused):
         return tuple(logits_shape)

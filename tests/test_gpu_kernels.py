@@ -633,3 +633,31 @@ def test_mod_route_bit_exact(K):
         np.testing.assert_array_equal(npy(owner), o)
         np.testing.assert_array_equal(npy(local), l)
         np.testing.assert_array_equal(npy(counts), np.bincount(o, minlength=8))
+
+
+@pytest.mark.parametrize("engine", ["ffma", "tcgen05"])
+@pytest.mark.parametrize("S,nc,nq,d,k", [(2, 10_007, 70, 64, 100), (8, 200_003, 300, 64, 100), (3, 3_001, 33, 32, 10)])
+def test_candidate_sharded_retrieval_equals_unsharded(K, S, nc, nq, d, k, engine):
+    """Candidates split row-wise into S contiguous shards, local exact top-k per shard with global ids, lists concatenated
+    in shard order and merged by krs_row_topk == the unsharded search, scores and ids exactly (same per-pair arithmetic,
+    ties -> lowest id)."""
+    K.ops.set_topk_engine(engine)          # the same score engine on both sides: identical per-pair arithmetic
+    try:
+        rng = np.random.default_rng(S)
+        q = rng.normal(size=(nq, d)).astype(np.float32)
+        c = rng.normal(size=(nc, d)).astype(np.float32)
+        c[nc // 2] = c[5]                                      # exact score ties across shards
+        tq, tc_ = dev(q), dev(c)
+        ref_s, ref_i = K.ops.top_k_scores(tq, tc_, None, k)
+        bounds = [nc * s // S for s in range(S + 1)]
+        parts = []
+        for s in range(S):
+            shard = K.layers.CandidateShardedRetrieval(tc_[bounds[s]:bounds[s + 1]], bounds[s], k=k)
+            parts.append(shard.local_top_k(tq))
+        ms, mi = K.layers.merge_top_k(torch.cat([p[0] for p in parts], dim=1), torch.cat([p[1] for p in parts], dim=1), k)
+        np.testing.assert_array_equal(npy(mi), npy(ref_i))
+        np.testing.assert_array_equal(npy(ms), npy(ref_s))
+        ref = q.astype(np.float64) @ c.astype(np.float64).T
+        _check_topk(ref, npy(ms), npy(mi), k)
+    finally:
+        K.ops.set_topk_engine("auto")
