@@ -299,6 +299,10 @@ enum { KRS_OPT_SGD = 0, KRS_OPT_ADAGRAD = 1, KRS_OPT_ADAM = 2, KRS_OPT_FTRL = 3 
 int krs_rows_apply(float* p, float* s1, float* s2, float* compact, const int32_t* uniq_rows, const uint32_t* n_unique,
                    int64_t cap_rows, int E, int kind, const float* hyper, uint32_t* touched_to_clear /*nullable*/,
                    int64_t nwords, void* stream);
+/* The same four rules from a gradient ARENA + touched bitmap (krs_gather_bwd's output; only touched rows are visited, the
+ * arena rows are re-zeroed, the bitmap cleared) or, with touched == NULL, from a dense gradient over all n elements. */
+int krs_opt_apply(float* p, float* s1, float* s2, float* g, uint32_t* touched /*nullable*/, int64_t n, int row_len, int kind,
+                  const float* hyper, void* stream);
 /* Dense-semantics AdamW (every row decays, examples/dcn.py:127) reading its gradient from the compact rows:
  * rows whose touched bit is clear have g = 0; compact rows are re-zeroed and the bitmap is cleared afterwards.
  * ever (nullable): the ever-touched bitmap of krs_adamw_cold, same meaning (ever |= touched is folded in). */

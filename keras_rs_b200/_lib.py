@@ -118,6 +118,7 @@ _sig("krs_xchg_grad_pull", C.c_int, C.POINTER(KrsXchg), i32, C.c_void_p, C.c_voi
      C.c_void_p)
 _sig("krs_rows_apply", C.c_int, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p, C.c_void_p, i64, i32, i32,
      C.POINTER(C.c_float), C.c_void_p, i64, C.c_void_p)
+_sig("krs_opt_apply", C.c_int, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p, i64, i32, i32, C.POINTER(C.c_float), C.c_void_p)
 _sig("krs_adamw_compact", C.c_int, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, i64, i32,
      C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, i64, C.c_void_p)
 _sig("krs_ipc_alloc", C.c_int, C.POINTER(C.c_void_p), C.c_size_t, C.c_void_p)
@@ -134,7 +135,7 @@ EXPORTED = [
     "krs_remove_accidental_hits", "krs_sampling_prob_correction", "krs_loss_fwd_bwd",
     "krs_adamw", "krs_adamw_cold", "krs_adam_hyper_advance", "krs_sgd_adagrad", "krs_mod_route",
     "krs_xchg_route_workspace_bytes", "krs_xchg_route", "krs_xchg_barrier", "krs_xchg_gather_push", "krs_slot_scan_blocks",
-    "krs_slot_scan", "krs_xchg_grad_pull", "krs_rows_apply", "krs_adamw_compact", "krs_ipc_alloc", "krs_ipc_open",
+    "krs_slot_scan", "krs_xchg_grad_pull", "krs_rows_apply", "krs_opt_apply", "krs_adamw_compact", "krs_ipc_alloc", "krs_ipc_open",
     "krs_ipc_close", "krs_ipc_free", "krs_enable_peer_access",
 ]
 

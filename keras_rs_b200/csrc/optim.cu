@@ -211,6 +211,59 @@ __global__ void __launch_bounds__(256) rows_apply_kernel(float* __restrict__ p, 
   }
 }
 
+// The same four rules straight from a gradient ARENA + touched bitmap (single-GPU tables, TableConfig.optimizer): the
+// warp walks 32 bitmap words, LPR-lane groups take the set rows one float4 column each, the arena row is re-zeroed and the
+// word cleared.  touched == nullptr: dense gradient, every element is visited (FTRL / Adam on ordinary variables).
+template <int KIND>
+__global__ void __launch_bounds__(256) rows_apply_arena_kernel(float* __restrict__ p, float* __restrict__ s1, float* __restrict__ s2,
+                                                               float* __restrict__ g, uint32_t* __restrict__ touched, int64_t nwords,
+                                                               int64_t nrows, int row_len, const RowsHyper H) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t w0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; w0 < nwords; w0 += nwarps * 32) {
+    const int64_t wi = w0 + lane;
+    const uint32_t word = wi < nwords ? touched[wi] : 0u;
+    unsigned nz = __ballot_sync(0xffffffffu, word != 0u);
+    while (nz) {
+      const int src = __ffs(nz) - 1;
+      nz &= nz - 1;
+      uint32_t bits = __shfl_sync(0xffffffffu, word, src);
+      while (bits) {
+        const int bit = __ffs(bits) - 1;
+        bits &= bits - 1;
+        const int64_t row = (w0 + src) * 32 + bit;
+        if (row >= nrows) break;
+        const int64_t base = row * (int64_t)row_len;
+        for (int c = lane; c < row_len; c += 32) {
+          const float gg = g[base + c];
+          float pv = p[base + c];
+          float a = KIND != KRS_OPT_SGD ? s1[base + c] : 0.f;
+          float b = (KIND == KRS_OPT_ADAM || KIND == KRS_OPT_FTRL) ? s2[base + c] : 0.f;
+          rows_update_one<KIND>(pv, a, b, gg, H);
+          p[base + c] = pv;
+          if (KIND != KRS_OPT_SGD) s1[base + c] = a;
+          if (KIND == KRS_OPT_ADAM || KIND == KRS_OPT_FTRL) s2[base + c] = b;
+          g[base + c] = 0.f;
+        }
+      }
+    }
+    if (wi < nwords && word != 0u) touched[wi] = 0u;
+  }
+}
+template <int KIND>
+__global__ void __launch_bounds__(256) dense_apply_kernel(float* __restrict__ p, float* __restrict__ s1, float* __restrict__ s2,
+                                                          const float* __restrict__ g, int64_t n, const RowsHyper H) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float pv = p[i];
+    float a = KIND != KRS_OPT_SGD ? s1[i] : 0.f;
+    float b = (KIND == KRS_OPT_ADAM || KIND == KRS_OPT_FTRL) ? s2[i] : 0.f;
+    rows_update_one<KIND>(pv, a, b, g[i], H);
+    p[i] = pv;
+    if (KIND != KRS_OPT_SGD) s1[i] = a;
+    if (KIND == KRS_OPT_ADAM || KIND == KRS_OPT_FTRL) s2[i] = b;
+  }
+}
+
 // adamw_vec_kernel<ARENA> with the gradient row fetched through the slot numbering of the touched bitmap.
 __global__ void __launch_bounds__(256) adamw_compact_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
                                                             float* __restrict__ compact, const uint32_t* __restrict__ touched,
@@ -405,5 +458,39 @@ extern "C" int krs_adamw_compact(float* p, float* m, float* v, float* compact, u
   } else {
     KRS_CUDA(cudaMemsetAsync(touched, 0, sizeof(uint32_t) * (size_t)nwords, s));
   }
+  return KRS_OK;
+}
+
+
+extern "C" int krs_opt_apply(float* p, float* s1, float* s2, float* g, uint32_t* touched, int64_t n, int row_len, int kind,
+                             const float* hyper, void* stream) {
+  KRS_REQUIRE(p && g && hyper, "krs_opt_apply: null argument");
+  KRS_REQUIRE(kind >= KRS_OPT_SGD && kind <= KRS_OPT_FTRL, "krs_opt_apply: unknown optimizer kind %d", kind);
+  KRS_REQUIRE(kind == KRS_OPT_SGD || s1 != nullptr, "krs_opt_apply: optimizer kind %d needs its first slot variable", kind);
+  KRS_REQUIRE((kind != KRS_OPT_ADAM && kind != KRS_OPT_FTRL) || s2 != nullptr, "krs_opt_apply: optimizer kind %d needs two slot variables", kind);
+  KRS_REQUIRE(touched == nullptr || (row_len > 0 && n % row_len == 0), "krs_opt_apply: arena needs n %% row_len == 0");
+  if (n == 0) return KRS_OK;
+  RowsHyper H;
+  for (int i = 0; i < 8; ++i) H.h[i] = hyper[i];
+  cudaStream_t s = as_stream(stream);
+  if (touched) {
+    const int64_t rows = n / row_len, nwords = ceil_div<int64_t>(rows, 32);
+    const unsigned grid = (unsigned)krs::imax<int64_t>(1, krs::imin<int64_t>(ceil_div<int64_t>(ceil_div<int64_t>(nwords, 32), 8), (int64_t)sm_count() * 16));
+    switch (kind) {
+      case KRS_OPT_SGD: rows_apply_arena_kernel<KRS_OPT_SGD><<<grid, 256, 0, s>>>(p, s1, s2, g, touched, nwords, rows, row_len, H); break;
+      case KRS_OPT_ADAGRAD: rows_apply_arena_kernel<KRS_OPT_ADAGRAD><<<grid, 256, 0, s>>>(p, s1, s2, g, touched, nwords, rows, row_len, H); break;
+      case KRS_OPT_ADAM: rows_apply_arena_kernel<KRS_OPT_ADAM><<<grid, 256, 0, s>>>(p, s1, s2, g, touched, nwords, rows, row_len, H); break;
+      default: rows_apply_arena_kernel<KRS_OPT_FTRL><<<grid, 256, 0, s>>>(p, s1, s2, g, touched, nwords, rows, row_len, H); break;
+    }
+  } else {
+    const unsigned grid = (unsigned)krs::imax<int64_t>(1, krs::imin<int64_t>(ceil_div<int64_t>(n, 256), (int64_t)sm_count() * 32));
+    switch (kind) {
+      case KRS_OPT_SGD: dense_apply_kernel<KRS_OPT_SGD><<<grid, 256, 0, s>>>(p, s1, s2, g, n, H); break;
+      case KRS_OPT_ADAGRAD: dense_apply_kernel<KRS_OPT_ADAGRAD><<<grid, 256, 0, s>>>(p, s1, s2, g, n, H); break;
+      case KRS_OPT_ADAM: dense_apply_kernel<KRS_OPT_ADAM><<<grid, 256, 0, s>>>(p, s1, s2, g, n, H); break;
+      default: dense_apply_kernel<KRS_OPT_FTRL><<<grid, 256, 0, s>>>(p, s1, s2, g, n, H); break;
+    }
+  }
+  KRS_LAUNCH_CHECK();
   return KRS_OK;
 }

@@ -12,6 +12,7 @@ from __future__ import annotations
 import dataclasses
 from typing import Any
 
+import numpy as np
 import torch
 
 from .. import _lib as L
@@ -66,6 +67,44 @@ class FeatureConfig:
         return cls(**config)
 
 
+def ragged_to_dense_inputs(inputs, weights=None, dense_row_length: int | None = None, device="cuda"):
+    """base_distributed_embedding.py:31-92 (_ragged_to_dense_inputs): a ragged batch of id lists (object ndarray, list of
+    lists, or a CSR pair `(values, row_splits)`) becomes a dense (B, L) id tensor padded with 0 and a float32 weight
+    tensor that is 0 on the padding (1, or the given weights, on real ids) — so `sum` / `mean` / `sqrtn` combiners see
+    exactly the ragged row.  L = dense_row_length or the longest row; longer rows are an error.  Non-ragged inputs are
+    returned unchanged.  The padding is built with one vectorised scatter (no per-row Python loop)."""
+    x, w = inputs, weights
+    csr = isinstance(x, tuple) and len(x) == 2 and not isinstance(x[0], (list, tuple)) and np.ndim(x[1]) == 1 and np.ndim(x[0]) == 1
+    if isinstance(x, torch.Tensor) or (isinstance(x, np.ndarray) and x.dtype != object):
+        return inputs, weights
+    if csr:
+        values, splits = np.asarray(x[0]), np.asarray(x[1]).astype(np.int64)
+        wvals = None if w is None else np.asarray(w[0] if isinstance(w, tuple) else w, dtype=np.float32).reshape(-1)
+    else:
+        rows = [np.asarray(r) for r in x]
+        if len(rows) == 0 or all(r.ndim == 0 for r in rows):
+            return inputs, weights                              # a plain list of scalars: not ragged
+        lens = np.array([len(r) for r in rows], dtype=np.int64)
+        splits = np.concatenate([[0], np.cumsum(lens)])
+        values = np.concatenate(rows) if splits[-1] else np.zeros((0,), np.int64)
+        wvals = None if w is None else np.concatenate([np.asarray(r, dtype=np.float32) for r in w])
+    lens = np.diff(splits)
+    B = len(lens)
+    L_ = int(dense_row_length) if dense_row_length is not None else (int(lens.max()) if B else 0)
+    if B and int(lens.max()) > L_:
+        raise ValueError(f"ragged row of length {int(lens.max())} exceeds the dense row length {L_}")
+    if wvals is not None and len(wvals) != len(values):
+        raise ValueError("ragged `weights` must have the same row lengths as `inputs`")
+    row = np.repeat(np.arange(B), lens)
+    col = np.arange(len(values)) - np.repeat(splits[:-1], lens)
+    ids = np.zeros((B, L_), dtype=values.dtype if values.dtype.kind in "iu" else np.int64)
+    ids[row, col] = values
+    wts = np.zeros((B, L_), dtype=np.float32)
+    wts[row, col] = 1.0 if wvals is None else wvals
+    ids_t = torch.from_numpy(ids if ids.dtype in (np.int32, np.int64) else ids.astype(np.int64))
+    return ids_t.to(device), torch.from_numpy(wts).to(device)
+
+
 def _flatten(struct, path=()):
     """Deterministic flattening of nested dict / list / tuple structures -> [(path, leaf)]."""
     if isinstance(struct, dict):
@@ -79,6 +118,34 @@ def _flatten(struct, path=()):
             out.extend(_flatten(v, path + (i,)))
         return out
     return [(path, struct)]
+
+
+def _is_ragged_leaf(v) -> bool:
+    if isinstance(v, torch.Tensor):
+        return False
+    if isinstance(v, np.ndarray):
+        return v.dtype == object
+    if isinstance(v, tuple) and len(v) == 2 and np.ndim(v[0]) == 1 and np.ndim(v[1]) == 1 and not isinstance(v[0], (list, tuple)):
+        return True                                            # CSR (values, row_splits)
+    return isinstance(v, (list, tuple)) and len(v) > 0 and isinstance(v[0], (list, tuple, np.ndarray))
+
+
+def _flatten_inputs(struct, flat_configs):
+    """Like _flatten, but stops at the leaves of the FEATURE structure (a ragged feature is itself a list of lists)."""
+    out = []
+    for path, _ in flat_configs:
+        cur = struct
+        for k in path:
+            cur = cur[k]
+        out.append((path, cur))
+    return out
+
+
+def _has_ragged(inputs, flat_configs) -> bool:
+    try:
+        return any(_is_ragged_leaf(v) for _, v in _flatten_inputs(inputs, flat_configs))
+    except (KeyError, IndexError, TypeError):
+        return False
 
 
 def _pack_like(struct, leaves_iter):
@@ -146,9 +213,19 @@ class DistributedEmbedding(Layer):
     def preprocess(self, inputs, weights=None, training: bool = False):
         """base_distributed_embedding.py:630-729: on the default device this is pure structure
         shuffling; it returns the dict form that `call` also accepts (:721-738)."""
-        d = {"inputs": {p: v for p, v in _flatten(inputs)}}
-        if weights is not None:
-            d["weights"] = {p: v for p, v in _flatten(weights)}
+        fin = {p: v for p, v in _flatten_inputs(inputs, self._flat)}
+        fw = None if weights is None else {p: v for p, v in _flatten_inputs(weights, self._flat)}
+        # ragged / CSR features are densified to their configured valence with a 0-weight mask (:862-908)
+        use_w = fw is not None
+        new_w = {}
+        for path, fc in self._flat:
+            valence = None if len(fc.input_shape) <= 1 else fc.input_shape[1]
+            x, w = ragged_to_dense_inputs(fin[path], None if fw is None else fw[path], valence, device=self._device)
+            use_w = use_w or (w is not None)
+            fin[path], new_w[path] = x, w
+        d = {"inputs": fin}
+        if use_w:
+            d["weights"] = new_w
         return {"preprocessed_inputs_per_placement": {"default_device": d}}
 
     def _check_shape(self, fc: FeatureConfig, ids: torch.Tensor):
@@ -164,6 +241,8 @@ class DistributedEmbedding(Layer):
             pp = inputs["preprocessed_inputs_per_placement"]["default_device"]
             flat_in = [pp["inputs"][p] for p, _ in self._flat]
             flat_w = [pp["weights"][p] for p, _ in self._flat] if "weights" in pp else None
+        elif _has_ragged(inputs, self._flat):
+            return self.call(self.preprocess(inputs, weights, training), training=training, concat=concat)
         else:
             fi = _flatten(inputs)
             if [p for p, _ in fi] != [p for p, _ in self._flat]:
@@ -201,6 +280,37 @@ class DistributedEmbedding(Layer):
             views.append(out[:, off:off + e])
             off += e
         return _pack_like(self.feature_configs, iter(views))
+
+    # ------------------------------------------------------------------ per-table optimizers (:172-186)
+    def table_optimizers(self):
+        """One optimizer per TableConfig, built from `TableConfig.optimizer` (a name or an instance).  The supported set is
+        the reference's (jax/config_conversion.py:211-288): SGD, Adagrad, Adam, Ftrl — in their row-sparse forms, i.e. only
+        rows that received gradient are touched (Adam is the per-row "lazy" form the SparseCore path applies)."""
+        from .. import optimizers as O_
+        if getattr(self, "_table_opts", None) is None:
+            opts = []
+            for t in self._tables:
+                o = t.optimizer
+                if isinstance(o, str):
+                    name = o.lower()
+                    if name not in ("sgd", "adagrad", "adam", "ftrl"):
+                        raise ValueError(f"Unsupported optimizer type {o!r}. Optimizer must be one of [Adagrad, Adam, Ftrl, SGD].")
+                    o = O_.Adam(sparse_rows=True) if name == "adam" else O_.get(name)
+                elif not isinstance(o, (O_.SGD, O_.Adagrad, O_.Adam, O_.Ftrl)) or type(o) is O_.AdamW:
+                    raise ValueError(f"Unsupported optimizer type {type(o)}. Optimizer must be one of [Adagrad, Adam, Ftrl, SGD].")
+                if isinstance(o, O_.Adam):
+                    o.sparse_rows = True
+                opts.append(o)
+            self._table_opts = opts
+        return self._table_opts
+
+    def apply_table_gradients(self) -> None:
+        """Applies every table's own optimizer to the gradient its arena received (needs sparse_grad_arena=True: the fused
+        backward leaves per-table gradient arenas + touched bitmaps instead of dense (V, E) gradients)."""
+        if not self.sparse_grad_arena:
+            raise ValueError("apply_table_gradients needs DistributedEmbedding(..., sparse_grad_arena=True)")
+        for p, opt in zip(self._table_params, self.table_optimizers()):
+            opt.apply([p])
 
     def get_config(self):
         c = super().get_config()

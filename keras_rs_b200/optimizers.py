@@ -79,6 +79,12 @@ class Optimizer:
         check(lib.krs_rows_apply(ptr(p), ptr(s1), ptr(s2), ptr(cs.compact), ptr(cs.uniq_rows), ptr(cs.n_unique),
                                  cs.cap_rows, p.shape[-1], kind, h, ptr(cs.touched), cs.touched.numel(), stream()))
 
+    def _opt_apply(self, p, g, touched, kind, hyper, s1=None, s2=None):
+        """krs_opt_apply: one of the four row rules from an arena (touched rows only) or a dense gradient."""
+        h = (C.c_float * 8)(*([float(x) for x in hyper] + [0.0] * (8 - len(hyper))))
+        row_len = p.shape[-1] if (touched is not None and p.dim() >= 2) else 1
+        check(lib.krs_opt_apply(ptr(p), ptr(s1), ptr(s2), ptr(g), ptr(touched), p.numel(), row_len, kind, h, stream()))
+
     def _update_compact(self, p, cs):
         """p: (rows, E) table shard; cs: CompactGrads (one gradient row per distinct touched row, in row order)."""
         raise NotImplementedError(f"{type(self).__name__} has no compact-row update")
@@ -94,6 +100,10 @@ class AdamW(Optimizer):
 
     def _update(self, p, g, touched):
         st = self._slots(p, ("m", "v"))
+        if getattr(self, "sparse_rows", False) and touched is not None:   # lazy Adam from the arena: touched rows only
+            self._opt_apply(p, g, touched, OPT_ADAM, [self.learning_rate, self.beta_1, self.beta_2, self.epsilon, self._alpha()],
+                            st["m"], st["v"])
+            return
         row_len = p.shape[-1] if (touched is not None and p.dim() >= 2) else 1
         ever = getattr(p, "_krs_ever", None) if touched is not None else None
         if ever is not None and not getattr(p, "_krs_ever_owner", None) in (None, id(self)):
@@ -180,10 +190,19 @@ class Ftrl(Optimizer):
         self.learning_rate_power, self.initial_accumulator_value = learning_rate_power, initial_accumulator_value
         self.l1, self.l2, self.beta = l1_regularization_strength, l2_regularization_strength, beta
 
-    def _update_compact(self, p, cs):
+    def _ftrl_state(self, p):
         st = self._state.get(id(p))
         if st is None:
             st = self._state[id(p)] = {"accum": torch.full_like(p, self.initial_accumulator_value), "linear": torch.zeros_like(p)}
+        return st
+
+    def _update(self, p, g, touched):
+        st = self._ftrl_state(p)
+        self._opt_apply(p, g, touched, OPT_FTRL, [self.learning_rate, self.learning_rate_power, self.l1, self.l2, self.beta],
+                        st["accum"], st["linear"])
+
+    def _update_compact(self, p, cs):
+        st = self._ftrl_state(p)
         self._rows_apply(p, cs, OPT_FTRL, [self.learning_rate, self.learning_rate_power, self.l1, self.l2, self.beta],
                          st["accum"], st["linear"])
 
