@@ -60,9 +60,19 @@ def bench_dot(reps):
         o.backward(gout)
 
     ms_fb = timed(fb, max(3, reps // 2))
+    # the backward kernel alone, through the C ABI (no autograd / allocation in the timed region)
+    import ctypes as C
+    dbufs = [torch.empty((B, N * E), device="cuda") for _ in range(2)]
+    fp = (C.c_void_p * N)(*[t.data_ptr() for t in feats])
+    fs = (C.c_int64 * N)(*[N * E] * N)
+    dps = [(C.c_void_p * N)(*[d[:, j * E:(j + 1) * E].data_ptr() for j in range(N)]) for d in dbufs]
+    ms_b = timed(lambda i: check(lib.krs_dot_bwd(fp, fs, ptr(gout), dps[i % 2], fs, N, E, B, 0, 0, stream())), reps)
+    by_b = 2 * B * N * E * 4 + B * 351 * 4                 # F read once, dF written once, G read
     return [dict(kernel="dot_fwd_mma_kernel", config="C3 N=27 E=128 B=65536 -> 351", ms=ms, GBps=by / ms * 1e-6, bytes=by,
                  frac_of_measured_hbm=by / ms * 1e-6 / peaks()["hbm_gbs"]),
-            dict(kernel="dot fwd+bwd (autograd path)", config="C3", ms=ms_fb)]
+            dict(kernel="dot_bwd_mma_kernel", config="C3 (C ABI call)", ms=ms_b, GBps=by_b / ms_b * 1e-6, bytes=by_b,
+                 frac_of_measured_hbm=by_b / ms_b * 1e-6 / peaks()["hbm_gbs"]),
+            dict(kernel="dot fwd+bwd (autograd path, incl. host overhead of 27 strided views)", config="C3", ms=ms_fb)]
 
 
 def bench_gather128(reps):

@@ -261,11 +261,26 @@ struct FeatSample {
   int nshards, i64, nchunk, hot, out_off, div_kind;   // div_kind: 0 none, 1 mean, 2 sqrtn
 };
 
-template <int HU>
-__global__ void __launch_bounds__(256) gather_sample_kernel(const __grid_constant__ GatherParams p, int lpr, int total_hot) {
+// cp.async (LDGSTS) row staging: row loads do not hold registers while they are in flight, so a warp keeps RING - HU rows
+// (24 x 512 B) outstanding with ~40 registers per thread; with register-resident loads (8 per warp at 76 registers) the same
+// walk reached 3.3 TB/s.  Ring slot = 32 lanes x 16 B; lane L stages its own 16 bytes of its group's row.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int SAMPLE_HU = 8;         // lookups per batch (one cp.async group)
+constexpr int SAMPLE_DEPTH = 4;      // batches in the ring: 3 in flight while 1 is consumed
+constexpr int SAMPLE_WARPS = 4;
+
+__global__ void __launch_bounds__(SAMPLE_WARPS * 32) gather_sample_kernel(const __grid_constant__ GatherParams p, int lpr, int total_hot) {
+  constexpr int HU = SAMPLE_HU, DEPTH = SAMPLE_DEPTH;
   __shared__ FeatSample sf[MAXF];
   __shared__ unsigned char lk_feat[SAMPLE_MAXL];
   __shared__ int first[MAXF + 1];
+  extern __shared__ __align__(16) float4 ring_all[];          // [warp][DEPTH * HU][32]
   for (int i = threadIdx.x; i < p.F; i += blockDim.x) {
     const krs_feature_t& f = p.f[i];
     FeatSample t;
@@ -292,62 +307,75 @@ __global__ void __launch_bounds__(256) gather_sample_kernel(const __grid_constan
   for (int i = threadIdx.x; i < p.F; i += blockDim.x)
     for (int l = first[i]; l < first[i + 1]; ++l) lk_feat[l] = (unsigned char)i;
   __syncthreads();
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane % lpr, gsub = lane / lpr;
   const int groups = 32 / lpr;
+  float4* ring = ring_all + (size_t)warp * (DEPTH * HU * 32);
+  const int nbatch = (total_hot + HU - 1) / HU;
   const int64_t ngroups = (((int64_t)gridDim.x * blockDim.x) >> 5) * groups;
-  for (int64_t b = ((((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * groups) + gsub; b < p.B; b += ngroups) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    float dsum = 0.f;
-    for (int l0 = 0; l0 < total_hot; l0 += HU) {
-      const float* src[HU];
-      float w[HU];
-      float4 v[HU];
-      int fe[HU];
+  // every lane of the warp runs the same number of sample iterations (cp.async groups are per thread, the ring is per warp)
+  const int64_t b_first = ((((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * groups);
+  for (int64_t b0 = b_first; b0 < p.B; b0 += ngroups) {
+    const int64_t b = b0 + gsub;
+    const bool live = b < p.B;
+    // stage one batch of lookups: ids -> row addresses -> cp.async of this lane's 16 bytes (or a NaN / nothing)
+    auto issue = [&](int bi) {
+      if (bi < nbatch && live) {
 #pragma unroll
-      for (int u = 0; u < HU; ++u) {
-        src[u] = nullptr;
-        w[u] = 1.f;
-        fe[u] = -1;
-        const int l = l0 + u;
-        if (l < total_hot) {
-          const int f = lk_feat[l];
-          const FeatSample& ft = sf[f];
-          fe[u] = f;
-          const int64_t idx = b * ft.stride + (l - first[f]);
-          const int64_t id = resolve_id(ft.i64 ? load_id<int64_t>(ft.ids, idx) : load_id<int32_t>(ft.ids, idx), ft.vocab);
-          if (ft.weights) w[u] = ft.weights[idx];
-          if (id < 0) src[u] = nan_row();
-          else if (sub < ft.nchunk) {
-            const int dim = ft.nchunk * 4;
-            src[u] = (ft.nshards > 1 ? ft.shards[(int)(id % ft.nshards)] + (id / ft.nshards) * (int64_t)dim : ft.table + id * (int64_t)dim) + sub * 4;
+        for (int u = 0; u < HU; ++u) {
+          const int l = bi * HU + u;
+          if (l < total_hot) {
+            const int f = lk_feat[l];
+            const FeatSample& ft = sf[f];
+            if (sub < ft.nchunk) {
+              const int64_t idx = b * ft.stride + (l - first[f]);
+              const int64_t id = resolve_id(ft.i64 ? load_id<int64_t>(ft.ids, idx) : load_id<int32_t>(ft.ids, idx), ft.vocab);
+              float4* slot = ring + ((bi % DEPTH) * HU + u) * 32 + lane;
+              if (id < 0) {
+                *slot = nan4();                        // no such row: NaN (jnp.take "fill") poisons the reduced sample
+              } else {
+                const int dim = ft.nchunk * 4;
+                const float* src = (ft.nshards > 1 ? ft.shards[(int)(id % ft.nshards)] + (id / ft.nshards) * (int64_t)dim
+                                                   : ft.table + id * (int64_t)dim) + sub * 4;
+                cp_async16(slot, src);
+              }
+            }
           }
         }
       }
+      cp_async_commit();                               // one (possibly empty) group per batch keeps the wait counts uniform
+    };
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float dsum = 0.f;
+#pragma unroll
+    for (int d = 0; d < DEPTH - 1; ++d) issue(d);
+    for (int bi = 0; bi < nbatch; ++bi) {
+      issue(bi + DEPTH - 1);
+      cp_async_wait<DEPTH - 1>();                      // batch bi has landed (this thread's own copies; the slot is lane-private)
+      if (!live) continue;
 #pragma unroll
       for (int u = 0; u < HU; ++u) {
-        if (src[u] == nan_row()) v[u] = nan4();        // no such row: NaN (jnp.take "fill") poisons the reduced sample
-        else if (src[u] != nullptr) v[u] = ldg_nc_f4(src[u]);
-        else v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-#pragma unroll
-      for (int u = 0; u < HU; ++u) {
-        if (fe[u] < 0) continue;
-        const FeatSample& ft = sf[fe[u]];
-        const int h = l0 + u - first[fe[u]];
+        const int l = bi * HU + u;
+        if (l >= total_hot) break;
+        const int f = lk_feat[l];
+        const FeatSample& ft = sf[f];
+        const int h = l - first[f];
+        if (sub >= ft.nchunk) continue;
+        const float4 v = ring[((bi % DEPTH) * HU + u) * 32 + lane];
+        const float w = ft.weights ? ft.weights[b * ft.stride + h] : 1.f;
         if (h == 0) {
           acc = make_float4(0.f, 0.f, 0.f, 0.f);
           dsum = 0.f;
         }
         // x = x * w ; sum over axis -2 in order h = 0..H-1 (no FMA contraction: embed_reduce.py:253,261)
         if (ft.hot == 1) {
-          acc.x = __fmul_rn(v[u].x, w[u]); acc.y = __fmul_rn(v[u].y, w[u]); acc.z = __fmul_rn(v[u].z, w[u]); acc.w = __fmul_rn(v[u].w, w[u]);
+          acc.x = __fmul_rn(v.x, w); acc.y = __fmul_rn(v.y, w); acc.z = __fmul_rn(v.z, w); acc.w = __fmul_rn(v.w, w);
         } else {
-          acc.x = __fadd_rn(acc.x, __fmul_rn(v[u].x, w[u])); acc.y = __fadd_rn(acc.y, __fmul_rn(v[u].y, w[u]));
-          acc.z = __fadd_rn(acc.z, __fmul_rn(v[u].z, w[u])); acc.w = __fadd_rn(acc.w, __fmul_rn(v[u].w, w[u]));
+          acc.x = __fadd_rn(acc.x, __fmul_rn(v.x, w)); acc.y = __fadd_rn(acc.y, __fmul_rn(v.y, w));
+          acc.z = __fadd_rn(acc.z, __fmul_rn(v.z, w)); acc.w = __fadd_rn(acc.w, __fmul_rn(v.w, w));
         }
-        if (ft.div_kind) dsum = ft.div_kind == 1 ? __fadd_rn(dsum, w[u]) : __fadd_rn(dsum, __fmul_rn(w[u], w[u]));
-        if (h == ft.hot - 1 && sub < ft.nchunk) {
+        if (ft.div_kind) dsum = ft.div_kind == 1 ? __fadd_rn(dsum, w) : __fadd_rn(dsum, __fmul_rn(w, w));
+        if (h == ft.hot - 1) {
           float4 r = acc;
           if (ft.div_kind) {
             const float div = ft.div_kind == 1 ? dsum : sqrtf(dsum);
@@ -360,6 +388,7 @@ __global__ void __launch_bounds__(256) gather_sample_kernel(const __grid_constan
         }
       }
     }
+    cp_async_wait<0>();
   }
 }
 
@@ -491,21 +520,34 @@ __global__ void __launch_bounds__(256) scatter_fast_kernel(const __grid_constant
     if (VEC) {
       const int sub = lane % (LPR > 0 ? LPR : 1), rsub = lane / (LPR > 0 ? LPR : 1);
       const int nlead = __popc(leaders);
-      for (int base = 0; base < nlead; base += RPW) {
-        const int nth = base + rsub;                     // this lane group's leader (nth set bit)
-        const bool act = nth < nlead;
-        const int r = act ? (int)__fns(leaders, 0, nth + 1) : 0;
-        const int64_t rid = __shfl_sync(0xffffffffu, id, r);
-        const unsigned rp = __shfl_sync(0xffffffffu, peers, r);
-        if (act) {
-          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-          for (unsigned q = rp; q; q &= q - 1) {
+      // U leaders per lane group and pass: their first gradient rows are in flight together (one load per lane and pass
+      // left the kernel latency-bound at 52 % of the HBM roofline); duplicates of a row, which are rare, follow serially.
+      constexpr int U = 4;
+      for (int base = 0; base < nlead; base += RPW * U) {
+        float4 acc[U];
+        int r[U];
+        int64_t rid[U];
+        unsigned rp[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int nth = base + u * RPW + rsub;                 // this lane group's leader (nth set bit)
+          const bool act = nth < nlead;
+          r[u] = act ? (int)__fns(leaders, 0, nth + 1) : 0;
+          rid[u] = __shfl_sync(0xffffffffu, id, r[u]);
+          rp[u] = __shfl_sync(0xffffffffu, peers, r[u]);
+          if (!act) r[u] = -1;
+          else acc[u] = ldg_nc_f4(gout + (b0 + r[u]) * p.out_ld + ft.out_offset + sub * 4);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (r[u] < 0) continue;
+          for (unsigned q = rp[u] & ~(1u << r[u]); q; q &= q - 1) {
             const int j = __ffs(q) - 1;
             const float4 v = ldg_nc_f4(gout + (b0 + j) * p.out_ld + ft.out_offset + sub * 4);
-            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            acc[u].x += v.x; acc[u].y += v.y; acc[u].z += v.z; acc[u].w += v.w;
           }
-          float* drow = (S > 1) ? ft.shard_grads[(int)(rid % S)] + (rid / S) * (int64_t)E : ft.grad + rid * (int64_t)E;
-          atomicAdd(reinterpret_cast<float4*>(drow + sub * 4), acc);
+          float* drow = (S > 1) ? ft.shard_grads[(int)(rid[u] % S)] + (rid[u] / S) * (int64_t)E : ft.grad + rid[u] * (int64_t)E;
+          atomicAdd(reinterpret_cast<float4*>(drow + sub * 4), acc[u]);
         }
       }
     } else {
@@ -714,8 +756,10 @@ extern "C" int krs_gather_fwd(const krs_feature_t* features, int F, int64_t B, f
   if (vec && variant != 3 && maxE <= 128 && total_hot <= SAMPLE_MAXL && F <= 255) {
     // flattened per-sample walk: a constant number of row loads in flight whatever the per-feature hotness
     const int64_t warps_needed = ceil_div<int64_t>(B, 32 / lpr);
-    const unsigned grid = (unsigned)krs::imax<int64_t>(1, krs::imin<int64_t>(ceil_div<int64_t>(warps_needed, 8), (int64_t)sm_count() * 64));
-    gather_sample_kernel<8><<<grid, 256, 0, s>>>(p, lpr, (int)total_hot);
+    const size_t smem = (size_t)SAMPLE_WARPS * SAMPLE_DEPTH * SAMPLE_HU * 32 * sizeof(float4);      // 64 KB: 3 CTAs per SM
+    KRS_CUDA(cudaFuncSetAttribute(gather_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned grid = (unsigned)krs::imax<int64_t>(1, krs::imin<int64_t>(ceil_div<int64_t>(warps_needed, SAMPLE_WARPS), (int64_t)sm_count() * 96));
+    gather_sample_kernel<<<grid, SAMPLE_WARPS * 32, smem, s>>>(p, lpr, (int)total_hot);
     KRS_LAUNCH_CHECK();
     return KRS_OK;
   }
