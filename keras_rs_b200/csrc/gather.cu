@@ -18,6 +18,8 @@
 // Backward: warp handles 32 consecutive samples of one feature; duplicate ids inside the warp are
 // found with __match_any_sync and their gradient rows summed in registers before one atomic per
 // (row, lane) — the scatter-add oracle is jax/test_utils.py:395-417.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace krs {
@@ -261,26 +263,25 @@ struct FeatSample {
   int nshards, i64, nchunk, hot, out_off, div_kind;   // div_kind: 0 none, 1 mean, 2 sqrtn
 };
 
-// cp.async (LDGSTS) row staging: row loads do not hold registers while they are in flight, so a warp keeps RING - HU rows
-// (24 x 512 B) outstanding with ~40 registers per thread; with register-resident loads (8 per warp at 76 registers) the same
-// walk reached 3.3 TB/s.  Ring slot = 32 lanes x 16 B; lane L stages its own 16 bytes of its group's row.
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// (A cp.async ring — 24 rows per warp in flight in shared memory — was tried and measured SLOWER, 4.31 ms against 2.45 ms
+// for register-resident loads with the same per-lookup address work: the walk was instruction-bound, not latency-bound.)
+// Per-lookup work is split like in gather_fast_kernel: ONE lane per lookup does the address work (id load, index rule,
+// MOD shard split, row address, weight), the row pointer and weight reach the other lanes of the group by shuffle, and the
+// per-lookup metadata every lane needs for the accumulate / finalize logic is one packed 8-byte shared-memory word.  (With
+// every lane redoing the address math — ~50 instructions and a dozen shared-memory reads per lookup — the walk sat at
+// 3.3-3.8 TB/s whatever the number of loads in flight.)
+struct LookupMeta {          // per flattened lookup l, built once per CTA
+  unsigned short feat;
+  unsigned char nchunk;      // float4 columns of the feature
+  unsigned char flags;       // 1: first lookup of its feature, 2: last, 4: hotness 1 (no add), 8: mean divisor, 16: sqrtn divisor
+  int out_off;
+};
 
-constexpr int SAMPLE_HU = 8;         // lookups per batch (one cp.async group)
-constexpr int SAMPLE_DEPTH = 4;      // batches in the ring: 3 in flight while 1 is consumed
-constexpr int SAMPLE_WARPS = 4;
-
-__global__ void __launch_bounds__(SAMPLE_WARPS * 32) gather_sample_kernel(const __grid_constant__ GatherParams p, int lpr, int total_hot) {
-  constexpr int HU = SAMPLE_HU, DEPTH = SAMPLE_DEPTH;
+template <int HU, int MINB>
+__global__ void __launch_bounds__(256, MINB) gather_sample_kernel(const __grid_constant__ GatherParams p, int lpr, int total_hot) {
   __shared__ FeatSample sf[MAXF];
-  __shared__ unsigned char lk_feat[SAMPLE_MAXL];
+  __shared__ LookupMeta meta[SAMPLE_MAXL];
   __shared__ int first[MAXF + 1];
-  extern __shared__ __align__(16) float4 ring_all[];          // [warp][DEPTH * HU][32]
   for (int i = threadIdx.x; i < p.F; i += blockDim.x) {
     const krs_feature_t& f = p.f[i];
     FeatSample t;
@@ -304,91 +305,95 @@ __global__ void __launch_bounds__(SAMPLE_WARPS * 32) gather_sample_kernel(const 
     first[p.F] = run;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < p.F; i += blockDim.x)
-    for (int l = first[i]; l < first[i + 1]; ++l) lk_feat[l] = (unsigned char)i;
+  for (int i = threadIdx.x; i < p.F; i += blockDim.x) {
+    const FeatSample& ft = sf[i];
+    for (int l = first[i]; l < first[i + 1]; ++l) {
+      LookupMeta m;
+      m.feat = (unsigned short)i;
+      m.nchunk = (unsigned char)ft.nchunk;
+      m.flags = (unsigned char)((l == first[i] ? 1 : 0) | (l == first[i + 1] - 1 ? 2 : 0) | (ft.hot == 1 ? 4 : 0) |
+                                (ft.div_kind == 1 ? 8 : 0) | (ft.div_kind == 2 ? 16 : 0));
+      m.out_off = ft.out_off;
+      meta[l] = m;
+    }
+  }
   __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
   const int sub = lane % lpr, gsub = lane / lpr;
   const int groups = 32 / lpr;
-  float4* ring = ring_all + (size_t)warp * (DEPTH * HU * 32);
-  const int nbatch = (total_hot + HU - 1) / HU;
+  const int gbase = gsub * lpr;                               // first lane of this group
+  const int RES = lpr < HU ? lpr : HU;                        // lookups resolved (one per lane of the group) per pass
   const int64_t ngroups = (((int64_t)gridDim.x * blockDim.x) >> 5) * groups;
-  // every lane of the warp runs the same number of sample iterations (cp.async groups are per thread, the ring is per warp)
-  const int64_t b_first = ((((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * groups);
-  for (int64_t b0 = b_first; b0 < p.B; b0 += ngroups) {
+  // all lanes of a warp iterate together (shuffles below): the warp-level loop runs while ANY group has a sample
+  for (int64_t b0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * groups; b0 < p.B; b0 += ngroups) {
     const int64_t b = b0 + gsub;
     const bool live = b < p.B;
-    // stage one batch of lookups: ids -> row addresses -> cp.async of this lane's 16 bytes (or a NaN / nothing)
-    auto issue = [&](int bi) {
-      if (bi < nbatch && live) {
-#pragma unroll
-        for (int u = 0; u < HU; ++u) {
-          const int l = bi * HU + u;
-          if (l < total_hot) {
-            const int f = lk_feat[l];
-            const FeatSample& ft = sf[f];
-            if (sub < ft.nchunk) {
-              const int64_t idx = b * ft.stride + (l - first[f]);
-              const int64_t id = resolve_id(ft.i64 ? load_id<int64_t>(ft.ids, idx) : load_id<int32_t>(ft.ids, idx), ft.vocab);
-              float4* slot = ring + ((bi % DEPTH) * HU + u) * 32 + lane;
-              if (id < 0) {
-                *slot = nan4();                        // no such row: NaN (jnp.take "fill") poisons the reduced sample
-              } else {
-                const int dim = ft.nchunk * 4;
-                const float* src = (ft.nshards > 1 ? ft.shards[(int)(id % ft.nshards)] + (id / ft.nshards) * (int64_t)dim
-                                                   : ft.table + id * (int64_t)dim) + sub * 4;
-                cp_async16(slot, src);
-              }
-            }
-          }
-        }
-      }
-      cp_async_commit();                               // one (possibly empty) group per batch keeps the wait counts uniform
-    };
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     float dsum = 0.f;
-#pragma unroll
-    for (int d = 0; d < DEPTH - 1; ++d) issue(d);
-    for (int bi = 0; bi < nbatch; ++bi) {
-      issue(bi + DEPTH - 1);
-      cp_async_wait<DEPTH - 1>();                      // batch bi has landed (this thread's own copies; the slot is lane-private)
-      if (!live) continue;
+    for (int l0 = 0; l0 < total_hot; l0 += RES) {
+      // ---- one lane per lookup: address work
+      const float* my_src = nullptr;
+      float my_w = 1.f;
+      if (live && sub < RES && l0 + sub < total_hot) {
+        const int l = l0 + sub;
+        const int f = meta[l].feat;
+        const FeatSample& ft = sf[f];
+        const int64_t idx = b * ft.stride + (l - first[f]);
+        const int64_t id = resolve_id(ft.i64 ? load_id<int64_t>(ft.ids, idx) : load_id<int32_t>(ft.ids, idx), ft.vocab);
+        if (ft.weights) my_w = ft.weights[idx];
+        if (id < 0) my_src = nan_row();
+        else {
+          const int dim = ft.nchunk * 4;
+          my_src = ft.nshards > 1 ? ft.shards[(int)(id % ft.nshards)] + (id / ft.nshards) * (int64_t)dim : ft.table + id * (int64_t)dim;
+        }
+      }
+      // ---- every lane: its float4 column of the RES rows, all loads issued before the first use
+      const float* src[HU];
+      float w[HU];
+      float4 v[HU];
 #pragma unroll
       for (int u = 0; u < HU; ++u) {
-        const int l = bi * HU + u;
-        if (l >= total_hot) break;
-        const int f = lk_feat[l];
-        const FeatSample& ft = sf[f];
-        const int h = l - first[f];
-        if (sub >= ft.nchunk) continue;
-        const float4 v = ring[((bi % DEPTH) * HU + u) * 32 + lane];
-        const float w = ft.weights ? ft.weights[b * ft.stride + h] : 1.f;
-        if (h == 0) {
+        src[u] = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, (unsigned long long)my_src, gbase + (u < RES ? u : 0)));
+        w[u] = __shfl_sync(0xffffffffu, my_w, gbase + (u < RES ? u : 0));
+        if (u >= RES || l0 + u >= total_hot) src[u] = nullptr;
+      }
+#pragma unroll
+      for (int u = 0; u < HU; ++u) {
+        if (src[u] == nullptr) continue;
+        if (src[u] == nan_row()) v[u] = nan4();            // no such row: NaN (jnp.take "fill") poisons the reduced sample
+        else if (sub < meta[l0 + u].nchunk) v[u] = ldg_nc_f4(src[u] + sub * 4);
+        else v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < HU; ++u) {
+        if (src[u] == nullptr) continue;
+        const LookupMeta m = meta[l0 + u];
+        if (m.flags & 1) {
           acc = make_float4(0.f, 0.f, 0.f, 0.f);
           dsum = 0.f;
         }
         // x = x * w ; sum over axis -2 in order h = 0..H-1 (no FMA contraction: embed_reduce.py:253,261)
-        if (ft.hot == 1) {
-          acc.x = __fmul_rn(v.x, w); acc.y = __fmul_rn(v.y, w); acc.z = __fmul_rn(v.z, w); acc.w = __fmul_rn(v.w, w);
+        if (m.flags & 4) {
+          acc.x = __fmul_rn(v[u].x, w[u]); acc.y = __fmul_rn(v[u].y, w[u]); acc.z = __fmul_rn(v[u].z, w[u]); acc.w = __fmul_rn(v[u].w, w[u]);
         } else {
-          acc.x = __fadd_rn(acc.x, __fmul_rn(v.x, w)); acc.y = __fadd_rn(acc.y, __fmul_rn(v.y, w));
-          acc.z = __fadd_rn(acc.z, __fmul_rn(v.z, w)); acc.w = __fadd_rn(acc.w, __fmul_rn(v.w, w));
+          acc.x = __fadd_rn(acc.x, __fmul_rn(v[u].x, w[u])); acc.y = __fadd_rn(acc.y, __fmul_rn(v[u].y, w[u]));
+          acc.z = __fadd_rn(acc.z, __fmul_rn(v[u].z, w[u])); acc.w = __fadd_rn(acc.w, __fmul_rn(v[u].w, w[u]));
         }
-        if (ft.div_kind) dsum = ft.div_kind == 1 ? __fadd_rn(dsum, w) : __fadd_rn(dsum, __fmul_rn(w, w));
-        if (h == ft.hot - 1) {
+        if (m.flags & 8) dsum = __fadd_rn(dsum, w[u]);
+        else if (m.flags & 16) dsum = __fadd_rn(dsum, __fmul_rn(w[u], w[u]));
+        if ((m.flags & 2) && sub < m.nchunk) {
           float4 r = acc;
-          if (ft.div_kind) {
-            const float div = ft.div_kind == 1 ? dsum : sqrtf(dsum);
+          if (m.flags & 24) {
+            const float div = (m.flags & 8) ? dsum : sqrtf(dsum);
             r.x = (div != 0.f) ? __fdiv_rn(r.x, div) : 0.f;   // divide_no_nan
             r.y = (div != 0.f) ? __fdiv_rn(r.y, div) : 0.f;
             r.z = (div != 0.f) ? __fdiv_rn(r.z, div) : 0.f;
             r.w = (div != 0.f) ? __fdiv_rn(r.w, div) : 0.f;
           }
-          stg_cs_f4(p.out + b * p.out_ld + ft.out_off + sub * 4, r);
+          stg_cs_f4(p.out + b * p.out_ld + m.out_off + sub * 4, r);
         }
       }
     }
-    cp_async_wait<0>();
   }
 }
 
@@ -756,10 +761,10 @@ extern "C" int krs_gather_fwd(const krs_feature_t* features, int F, int64_t B, f
   if (vec && variant != 3 && maxE <= 128 && total_hot <= SAMPLE_MAXL && F <= 255) {
     // flattened per-sample walk: a constant number of row loads in flight whatever the per-feature hotness
     const int64_t warps_needed = ceil_div<int64_t>(B, 32 / lpr);
-    const size_t smem = (size_t)SAMPLE_WARPS * SAMPLE_DEPTH * SAMPLE_HU * 32 * sizeof(float4);      // 64 KB: 3 CTAs per SM
-    KRS_CUDA(cudaFuncSetAttribute(gather_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const unsigned grid = (unsigned)krs::imax<int64_t>(1, krs::imin<int64_t>(ceil_div<int64_t>(warps_needed, SAMPLE_WARPS), (int64_t)sm_count() * 96));
-    gather_sample_kernel<<<grid, SAMPLE_WARPS * 32, smem, s>>>(p, lpr, (int)total_hot);
+    const unsigned grid = (unsigned)krs::imax<int64_t>(1, krs::imin<int64_t>(ceil_div<int64_t>(warps_needed, 8), (int64_t)sm_count() * 64));
+    // 4 lookups per pass, <= 40 registers, 6 CTAs per SM: the best of the measured variants (1.58 ms = 5.16 TB/s at the
+    // ml_perf shape; 8 lookups per pass at 3 or 4 CTAs per SM: 1.63 / 1.68 ms — profiles/r2_multihot_gather_variants.txt)
+    gather_sample_kernel<4, 6><<<grid, 256, 0, s>>>(p, lpr, (int)total_hot);
     KRS_LAUNCH_CHECK();
     return KRS_OK;
   }
