@@ -117,13 +117,21 @@ def run_reference(a):
     from oracle import torch_ref as T
     cores = T.usable_cores()        # min(cpu_count, affinity, cgroup quota): the threads the host really grants
     units = tuple(int(u) for u in a.dense_units.split(",") if u)
-    r = T.time_reference_arm(B=a.batch, F=a.features, V=a.vocab or 1_000_000, E=a.embed_dim, L=a.cross_layers, units=units,
+    # the same workload our arm runs at this N: global batch = batch x N; c2 default = constant rows per shard (vocab x N)
+    world = max(int(a.gpus), 1)
+    if a.workload == "c5":
+        V = a.vocab or c5_vocab(world)
+    else:
+        V = (a.vocab or 1_000_000) * (world if (world > 1 and not a.fixed_global_vocab and a.workload == "c2") else 1)
+    r = T.time_reference_arm(B=a.batch * world, F=a.features, V=V, E=a.embed_dim, L=a.cross_layers, units=units,
                              steps=a.steps, warmup=a.warmup, optimizer=a.optimizer, threads=cores, budget_s=max(a.cpu_budget_s, 240.0))
+    par = f"dp{world}" + ("" if world == 1 else "+mod-row-sharded tables (our arm); the reference arm runs the global batch on the host CPU")
     line = {
         "impl": "reference", "metric": "examples/sec", "value": r["value"], "unit": "examples/s", "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a), "global_batch": a.batch},
+        "config": {"workload": workload_name(a, world, V), "global_batch": a.batch * world, "parallelism": par, "gemm_engine": "cpu (torch / MKL)",
+                   "l2": "inputs_larger_than_L2", "final_loss": None, "launch": "host", "rows_per_gpu": None},
         "cpu_baseline": {"value": r["value"], "unit": "examples/s", "cores": cores, "kind": "port",
                          "sample": r["sample"] + " (torch-CPU restatement of the Keras op sequence on all host cores; "
                                                  "keras/jax not installable)"},

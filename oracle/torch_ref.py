@@ -149,13 +149,16 @@ def time_cpu_baseline(B=65536, F=26, V=1_000_000, E=32, L=3, units=(192, 192), s
 
 
 def time_reference_arm(B=65536, F=26, V=1_000_000, E=32, L=3, units=(192, 192), steps=20, warmup=5, optimizer="adamw",
-                       threads=None, seed=1234, budget_s=240.0):
-    """`bench.py --impl reference`: EXACTLY `warmup` untimed + `steps` timed steps.  The first warm-up step runs the full
-    workload and is timed; if warmup + steps of them fit `budget_s` the whole run is full size.  Otherwise every step is
-    a bounded sample of the same workload: batch AND vocabulary shrunk by the same power-of-two factor, which keeps the
-    per-example cost (dense layers per example + the dense optimizer sweep per example, V*F*E/B) unchanged."""
+                       threads=None, seed=1234, budget_s=240.0, mem_cap_bytes=24e9):
+    """`bench.py --impl reference`: EXACTLY `warmup` untimed + `steps` timed steps.  Every step is the full workload when
+    `warmup + steps` of them fit `budget_s` (and the tables + optimizer state + dense gradients fit `mem_cap_bytes` of host
+    memory); otherwise every step is a bounded sample of the same workload: batch AND vocabulary shrunk by the same
+    power-of-two factor, which keeps the per-example cost (dense layers per example + the dense optimizer sweep per
+    example, V*F*E/B) unchanged.  The factor is found by timing one step at each candidate size (that step counts as the
+    first warm-up step of the size finally used)."""
     threads = threads or usable_cores()
     torch.set_num_threads(threads)
+    slots = {"adamw": 4, "adagrad": 3, "sgd": 2}.get(optimizer, 4)          # p + grad (+ m, v | acc), fp32
 
     def build(scale):
         b, v = max(int(B * scale), 64), max(int(V * scale), 64)
@@ -171,23 +174,28 @@ def time_reference_arm(B=65536, F=26, V=1_000_000, E=32, L=3, units=(192, 192), 
         model.train_step(ids, y)
         return time.perf_counter() - t0
 
-    model, b, v = build(1.0)
-    t1 = one(model, b, v)
-    done_warm = 1
     scale = 1.0
-    need = t1 * (steps + max(warmup, 1) - 1)
-    if need > budget_s:
-        while scale > 1.0 / 4096 and t1 * scale * (steps + warmup) > budget_s:
-            scale /= 2
-        del model
+    while scale > 1.0 / 65536 and F * V * scale * E * 4.0 * slots > mem_cap_bytes:
+        scale /= 2
+    probes = []
+    while True:
         model, b, v = build(scale)
-        done_warm = 0
-    for _ in range(max(warmup - done_warm, 0)):
+        t1 = one(model, b, v)
+        probes.append((scale, t1))
+        if t1 * (steps + max(warmup, 1) - 1) <= budget_s or scale <= 1.0 / 65536:
+            break
+        need = t1 * (steps + warmup) / budget_s
+        del model
+        while need > 1.0 and scale > 1.0 / 65536:
+            scale /= 2
+            need /= 2
+    for _ in range(max(warmup - 1, 0)):
         one(model, b, v)
     times = [one(model, b, v) for _ in range(steps)]
     sec = sum(times) / len(times)
     sample = (f"every step = the full batch of {B} examples over the full {F} x {V}-row tables" if scale == 1.0 else
               f"every step = a 1/{int(round(1 / scale))} sample: batch {b} over {F} x {v}-row tables (batch and vocabulary shrunk "
-              f"together so the per-example cost incl. the dense optimizer sweep is unchanged; one full-size step took {t1:.1f} s)")
+              f"together so the per-example cost incl. the dense optimizer sweep is unchanged; probe steps: "
+              + ", ".join(f"1/{int(round(1 / sc))}: {t:.2f} s" for sc, t in probes) + ")")
     return dict(value=b / sec, cores=threads, steps=steps, warmup=warmup, ms_per_step=sec * 1e3, batch=b, vocab=v, scale=scale,
-                sample=sample, full_step_s=t1)
+                sample=sample)
