@@ -194,3 +194,60 @@ def test_cuda_graph_step_matches_eager_step(opt_name):
     assert o1.iterations == o2.iterations == 5
     assert_close(npy(m2.emb), npy(m1.emb), rel=1e-6, what="emb after 5 graph steps")
     assert_close(npy(m2.dense_flat), npy(m1.dense_flat), rel=1e-6, what="dense params after 5 graph steps")
+
+
+@pytest.mark.parametrize("opt_name", ["adamw", "adagrad", "sgd"])
+@pytest.mark.parametrize("sparse_arena", [False, True])
+def test_layer_api_forward_backward_apply_updates_the_tables(opt_name, sparse_arena):
+    """The drop-in path a user writes — model(ids) -> loss.backward() -> optimizer.apply(model.parameters()) — must update the
+    embedding tables from whichever gradient the backward produced (dense .grad by default, the arena with
+    sparse_arena=True), for every optimizer (round-1 advisor finding: the arena was preferred even when it was empty)."""
+    import keras_rs_b200 as K
+    from oracle import parity as PAR
+    rng = np.random.default_rng(9)
+    vocab, E, B = [40, 23, 64], 8, 64
+    m = _mk(vocab, E, 2, None, (16,), seed=4, dense_activation="tanh")
+    init = [npy(t).copy() for t in m.tables()]
+    tr = PAR.OracleTrainer(PAR.params_of(init, m.cross, m.mlp), opt_name, lr=0.05)
+    opt = {"adamw": K.optimizers.AdamW, "adagrad": K.optimizers.Adagrad, "sgd": K.optimizers.SGD}[opt_name](0.05)
+    for step in range(3):
+        ids = np.stack([rng.integers(0, v, size=B) for v in vocab], axis=1).astype(np.int32)
+        y = rng.uniform(size=B).astype(np.float32)
+        ref_loss = tr.train(ids.astype(np.int64), y)
+        params = list(m.parameters())
+        opt.zero_grad(params)
+        pred = m(dev(ids), sparse_arena=sparse_arena)
+        loss = K.ops.loss_fn(pred, dev(y), "mse")
+        loss.backward()
+        opt.apply(params)
+        assert abs(float(loss) - ref_loss) <= 1e-5 * max(abs(ref_loss), 1e-6)
+    rel = 5e-5 if opt_name == "adamw" else 1e-5
+    for f, t in enumerate(m.tables()):
+        assert_close(npy(t), tr.P["tables"][f], rel=rel, what=f"table {f} ({opt_name}, arena={sparse_arena})")
+        assert float(np.abs(npy(t) - init[f]).max()) > 1e-4            # the tables really moved
+    for c, pc in zip(m.cross, tr.P["cross"]):
+        assert_close(npy(c.kernel), pc["V"], rel=rel, what="cross V")
+
+
+def test_dense_swish_trains():
+    """Dense(activation='swish') forward and backward (round-1 advisor finding: the backward raised)."""
+    import keras_rs_b200 as K
+    rng = np.random.default_rng(2)
+    x = rng.normal(size=(33, 12)).astype(np.float32)
+    layer = K.layers.Dense(7, activation="swish")
+    tx = dev(x).requires_grad_(True)
+    y = layer(tx)
+    W, b = npy(layer.kernel), npy(layer.bias)
+    z = x @ W + b
+    assert_close(npy(y), z / (1.0 + np.exp(-z)), rel=1e-5, what="swish forward")
+    y.sum().backward()
+    s = 1.0 / (1.0 + np.exp(-z))
+    dz = s * (1.0 + z * (1.0 - s))
+    assert_close(npy(tx.grad), dz @ W.T, rel=1e-5, what="swish dx")
+    assert_close(npy(layer.kernel.grad), x.T @ dz, rel=1e-5, what="swish dW")
+
+
+def test_sharded_model_rejects_unaligned_embedding_dim():
+    from keras_rs_b200.sharded import ShardedDCN
+    with pytest.raises(ValueError, match="multiple of 4"):
+        ShardedDCN([10, 10], rank=0, world=1, sim=True, embedding_dim=6)
