@@ -77,8 +77,10 @@ class DLRM(torch.nn.Module):
         emb = ops.gather_concat([dict(table=self.tables[f], ids=ids[:, f], weights=None, combiner="sum") for f in range(self.F)],
                                 sparse_arena=sparse_arena)                      # (B, F*E): lookup + concat in one kernel
         if self.interaction == "dot":
-            feats = [h] + [emb[:, f * self.E:(f + 1) * self.E] for f in range(self.F)]
-            x = torch.cat([h, self.dot(feats)], dim=-1)
+            # one (B, (F+1)*E) buffer [bottom | e_1 .. e_F]: DotInteraction reads its features as strided views of it and its
+            # backward writes ONE gradient buffer (ops.dot_interaction_packed) — same kernels, same order as DotInteraction()(list)
+            packed = torch.cat([h, emb], dim=-1)
+            x = torch.cat([h, ops.dot_interaction_packed(packed, self.F + 1, self.E)], dim=-1)
         else:
             x0 = torch.cat([h, emb], dim=-1)                                    # model.py:204-207
             x = x0

@@ -266,6 +266,17 @@ class _DenseFn(torch.autograd.Function):
     def forward(ctx, x, W, b, act):
         B, K = x.shape
         N = W.shape[1]
+        ctx.K = K
+        if K % 4 != 0 and K > 64 and lib.krs_get_gemm_engine() != 0:
+            # TMA needs 16-byte row strides: a width like DLRM's 128 + 351 = 479 would fall back to the FFMA engine (measured
+            # 2.13 ms vs 0.31 ms for the forward at B = 65536, N = 1024).  Zero-pad x and W to the next multiple of 4; the
+            # padded column / row contribute exact zeros, and the caller still sees (B, K) / (K, N) shapes and gradients.
+            K4 = (K + 3) // 4 * 4
+            xp = torch.zeros((B, K4), device=x.device, dtype=torch.float32)
+            xp[:, :K] = x
+            Wp = torch.zeros((K4, N), device=W.device, dtype=torch.float32)
+            Wp[:K] = W
+            x, W, K = xp, Wp, K4
         y = torch.empty((B, N), device=x.device, dtype=torch.float32)
         check(lib.krs_dense_fwd(ptr(x), ptr(W), ptr(b), act, ptr(y), B, K, N, stream()))
         ctx.save_for_backward(x, W, b, y)
@@ -284,6 +295,9 @@ class _DenseFn(torch.autograd.Function):
         dz = torch.empty_like(gy)
         check(lib.krs_dense_bwd(ptr(gy), ptr(x), ptr(W), ptr(y), ctx.act, ptr(dx), ptr(dW), ptr(db), ptr(dz), B, K, N,
                                 stream()))
+        if K != ctx.K:                                      # padded width: hand back the caller's shapes
+            dx = dx[:, :ctx.K] if dx is not None else None
+            dW = dW[:ctx.K]
         return dx, dW, db, None
 
 
@@ -352,6 +366,44 @@ class _DotFn(torch.autograd.Function):
 
 def dot_interaction(inputs, self_interaction: bool, skip_gather: bool):
     return _DotFn.apply(self_interaction, skip_gather, *inputs)
+
+
+class _DotPackedFn(torch.autograd.Function):
+    """DotInteraction over the n features of ONE (B, n*E) buffer (feature j = columns j*E .. (j+1)*E): the same kernels
+    with pointer + row stride per feature, but a single autograd input — the backward writes one (B, n*E) gradient
+    instead of n tensors that autograd would each embed into a zero-filled full-size buffer (27 x 0.9 GB at C3)."""
+
+    @staticmethod
+    def forward(ctx, x, n, E, self_interaction, skip_gather):
+        x = _c(x)
+        B = x.shape[0]
+        out_dim = n * n if skip_gather else (n * (n + 1) // 2 if self_interaction else n * (n - 1) // 2)
+        out = torch.empty((B, out_dim), device=x.device, dtype=torch.float32)
+        ptrs = (C.c_void_p * n)(*[x.data_ptr() + 4 * j * E for j in range(n)])
+        strides = (C.c_int64 * n)(*[n * E] * n)
+        check(lib.krs_dot_fwd(ptrs, strides, n, E, B, int(self_interaction), int(skip_gather), ptr(out), stream()))
+        ctx.save_for_backward(x)
+        ctx.cfg = (n, E, self_interaction, skip_gather)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        (x,) = ctx.saved_tensors
+        n, E, self_interaction, skip_gather = ctx.cfg
+        gout = _c(gout)
+        B = x.shape[0]
+        dx = torch.empty_like(x)
+        ptrs = (C.c_void_p * n)(*[x.data_ptr() + 4 * j * E for j in range(n)])
+        gptrs = (C.c_void_p * n)(*[dx.data_ptr() + 4 * j * E for j in range(n)])
+        strides = (C.c_int64 * n)(*[n * E] * n)
+        check(lib.krs_dot_bwd(ptrs, strides, ptr(gout), gptrs, strides, n, E, B, int(self_interaction), int(skip_gather), stream()))
+        return dx, None, None, None, None
+
+
+def dot_interaction_packed(x: torch.Tensor, n: int, E: int, self_interaction: bool = False, skip_gather: bool = False):
+    if x.dim() != 2 or x.shape[1] != n * E:
+        raise ValueError(f"dot_interaction_packed: expected a (B, {n * E}) buffer, got {tuple(x.shape)}")
+    return _DotPackedFn.apply(x, n, E, self_interaction, skip_gather)
 
 
 # ----------------------------------------------------------------------------- retrieval

@@ -661,3 +661,46 @@ def test_candidate_sharded_retrieval_equals_unsharded(K, S, nc, nq, d, k, engine
         _check_topk(ref, npy(ms), npy(mi), k)
     finally:
         K.ops.set_topk_engine("auto")
+
+
+def test_dense_with_a_width_that_is_not_a_multiple_of_4_runs_on_the_tensor_pipe(K):
+    """Dense over K = 70 inputs (DLRM's top MLP sees 128 + 351 = 479): zero-padded to 72 inside the autograd function so
+    that the tcgen05 engine takes it; shapes and gradients the caller sees are the unpadded ones."""
+    rng = np.random.default_rng(8)
+    B, Kd, Nn = 256, 70, 32
+    x = rng.normal(size=(B, Kd)).astype(np.float32)
+    K.set_gemm_engine("tcgen05_ts")
+    try:
+        layer = K.layers.Dense(Nn, activation="relu")
+        tx = dev(x).requires_grad_(True)
+        before = K._lib.lib.krs_gemm_tc_launch_count()
+        y = layer(tx)
+        assert K._lib.lib.krs_gemm_tc_launch_count() > before, "the padded GEMM did not reach the tensor-pipe kernel"
+        W, b = npy(layer.kernel), npy(layer.bias)
+        z = x.astype(np.float64) @ W.astype(np.float64) + b
+        assert_close(npy(y), np.maximum(z, 0), rel=2e-5, what="padded dense fwd")
+        g = rng.normal(size=(B, Nn)).astype(np.float32)
+        y.backward(dev(g))
+        dz = g * (z > 0)
+        assert tuple(tx.grad.shape) == (B, Kd) and tuple(layer.kernel.grad.shape) == (Kd, Nn)
+        assert_close(npy(tx.grad), dz @ W.T.astype(np.float64), rel=2e-5, what="padded dense dx")
+        assert_close(npy(layer.kernel.grad), x.T.astype(np.float64) @ dz, rel=2e-5, what="padded dense dW")
+    finally:
+        K.set_gemm_engine("ffma")
+
+
+@pytest.mark.parametrize("self_i,skip", [(False, False), (True, True)])
+def test_dot_interaction_packed_equals_the_list_form(K, self_i, skip):
+    rng = np.random.default_rng(4)
+    B, n, E = 77, 5, 32
+    buf = rng.normal(size=(B, n * E)).astype(np.float32)
+    t1 = dev(buf).requires_grad_(True)
+    feats = [t1[:, j * E:(j + 1) * E] for j in range(n)]
+    o1 = K.layers.DotInteraction(self_interaction=self_i, skip_gather=skip)(feats)
+    t2 = dev(buf).requires_grad_(True)
+    o2 = K.ops.dot_interaction_packed(t2, n, E, self_i, skip)
+    np.testing.assert_array_equal(npy(o1), npy(o2))
+    g = dev(rng.normal(size=tuple(o1.shape)).astype(np.float32))
+    o1.backward(g)
+    o2.backward(g)
+    np.testing.assert_array_equal(npy(t1.grad), npy(t2.grad))
