@@ -12,7 +12,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libkrs_b200.so")
+# KRS_B200_LIB: alternate build of the same library (e.g. the -DKRS_TC_TRACE=1 build tests/tc_trace.py needs); debug only
+LIB_PATH = os.environ.get("KRS_B200_LIB") or os.path.join(_HERE, "lib", "libkrs_b200.so")
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
