@@ -115,7 +115,7 @@ def bench_multihot(reps):
     ms = timed(lambda i: plan.forward(out), reps)
     n_lookups = B * sum(MLPERF_HOT)
     by = n_lookups * E * 4 + B * len(vocab) * E * 4 + n_lookups * 8
-    res.append(dict(kernel="gather_generic_kernel (multi-hot)", config=f"ml_perf 26 features, sum(H)=214, E=128, B={B}, int64 ids, sum",
+    res.append(dict(kernel="gather_sample_kernel (multi-hot)", config=f"ml_perf 26 features, sum(H)=214, E=128, B={B}, int64 ids, sum",
                     ms=ms, GBps=by / ms * 1e-6, bytes=by, frac_of_measured_hbm=by / ms * 1e-6 / peaks()["hbm_gbs"]))
     # backward (scatter-add of the (B, F*E) gradient into the 214 rows of every sample)
     grads = [torch.zeros_like(t) for t in tables]
@@ -123,7 +123,7 @@ def bench_multihot(reps):
     gout = torch.randn((B, len(vocab) * E), device="cuda", generator=g)
     ms_b = timed(lambda i: plan.backward(gout, grads, touched), max(3, reps // 2))
     by_b = B * len(vocab) * E * 4 + 2 * n_lookups * E * 4 + n_lookups * 8
-    res.append(dict(kernel="scatter_generic_kernel (multi-hot)", config="same", ms=ms_b, GBps=by_b / ms_b * 1e-6, bytes=by_b,
+    res.append(dict(kernel="scatter_sample_kernel (multi-hot)", config="same", ms=ms_b, GBps=by_b / ms_b * 1e-6, bytes=by_b,
                     frac_of_measured_hbm=by_b / ms_b * 1e-6 / peaks()["hbm_gbs"]))
     return res
 

@@ -628,6 +628,124 @@ __global__ void __launch_bounds__(256) scatter_generic_kernel(const __grid_const
   }
 }
 
+// Multi-hot backward, the mirror of gather_sample_kernel: lane group per SAMPLE, the sample's lookups walked as one flattened
+// sequence, ONE lane per lookup does the address work (id, index rule, coefficient w / divisor, destination row, touched
+// bit), pointer + coefficient reach the group by shuffle, every lane issues one 16-byte reduction per lookup; the sample's
+// gradient chunk of a feature is loaded once and reused for all its lookups.  (The warp-per-(sample, feature) kernel above
+// keeps one row in flight per warp for the one-hot majority of the ml_perf list and repeats the address math in 32 lanes.)
+struct FeatScatter {
+  float* grad;
+  float* const* shard_grads;
+  uint32_t* touched;
+  uint32_t* const* shard_touched;
+  const void* ids;
+  const float* weights;      // nullptr unless honoured
+  long long vocab, stride;
+  int nshards, i64, nchunk, hot, out_off, div_kind;
+};
+
+__global__ void __launch_bounds__(256, 4) scatter_sample_kernel(const __grid_constant__ GatherParams p, int lpr, int total_hot) {
+  constexpr int HU = 4;
+  __shared__ FeatScatter sf[MAXF];
+  __shared__ LookupMeta meta[SAMPLE_MAXL];
+  __shared__ int first[MAXF + 1];
+  for (int i = threadIdx.x; i < p.F; i += blockDim.x) {
+    const krs_feature_t& f = p.f[i];
+    FeatScatter t;
+    t.grad = f.grad;
+    t.shard_grads = f.shard_grads;
+    t.touched = f.touched;
+    t.shard_touched = f.shard_touched;
+    t.ids = f.ids;
+    t.weights = (f.weights != nullptr && (f.reduce || f.combiner == KRS_COMBINER_SUM)) ? f.weights : nullptr;
+    t.vocab = f.vocab;
+    t.stride = f.ids_stride;
+    t.nshards = f.num_shards;
+    t.i64 = f.ids_i64;
+    t.nchunk = f.dim / 4;
+    t.hot = f.hotness;
+    t.out_off = f.out_offset;
+    t.div_kind = (f.reduce && f.combiner != KRS_COMBINER_SUM) ? (f.combiner == KRS_COMBINER_MEAN ? 1 : 2) : 0;
+    sf[i] = t;
+  }
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int i = 0; i < p.F; ++i) { first[i] = run; run += p.f[i].hotness; }
+    first[p.F] = run;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < p.F; i += blockDim.x) {
+    const FeatScatter& ft = sf[i];
+    for (int l = first[i]; l < first[i + 1]; ++l) {
+      LookupMeta m;
+      m.feat = (unsigned short)i;
+      m.nchunk = (unsigned char)ft.nchunk;
+      m.flags = (unsigned char)(l == first[i] ? 1 : 0);
+      m.out_off = ft.out_off;
+      meta[l] = m;
+    }
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % lpr, gsub = lane / lpr;
+  const int groups = 32 / lpr;
+  const int gbase = gsub * lpr;
+  const int RES = lpr < HU ? lpr : HU;
+  const float* __restrict__ gout = p.out;
+  const int64_t ngroups = (((int64_t)gridDim.x * blockDim.x) >> 5) * groups;
+  for (int64_t b0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * groups; b0 < p.B; b0 += ngroups) {
+    const int64_t b = b0 + gsub;
+    const bool live = b < p.B;
+    float4 gcur = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int l0 = 0; l0 < total_hot; l0 += RES) {
+      float* my_dst = nullptr;
+      float my_coef = 0.f;
+      if (live && sub < RES && l0 + sub < total_hot) {
+        const int l = l0 + sub;
+        const int f = meta[l].feat;
+        const FeatScatter& ft = sf[f];
+        const int64_t base = b * ft.stride;
+        const int64_t idx = base + (l - first[f]);
+        const int64_t id = resolve_id(ft.i64 ? load_id<int64_t>(ft.ids, idx) : load_id<int32_t>(ft.ids, idx), ft.vocab);
+        float coef = ft.weights ? ft.weights[idx] : 1.f;
+        if (ft.div_kind) {                                  // mean / sqrtn: the feature's divisor (rare on this path)
+          float d = 0.f;
+          for (int h = 0; h < ft.hot; ++h) {
+            const float w = ft.weights ? ft.weights[base + h] : 1.f;
+            d += ft.div_kind == 1 ? w : w * w;
+          }
+          if (ft.div_kind == 2) d = sqrtf(d);
+          coef *= d != 0.f ? 1.f / d : 0.f;
+        }
+        if (id >= 0 && coef != 0.f) {                       // ids that address no row receive no gradient
+          const int dim = ft.nchunk * 4;
+          if (ft.nshards > 1) {
+            const int o = (int)(id % ft.nshards);
+            const int64_t lr = id / ft.nshards;
+            my_dst = ft.shard_grads[o] + lr * (int64_t)dim;
+            if (ft.shard_touched) atomicOr(ft.shard_touched[o] + (lr >> 5), 1u << (lr & 31));
+          } else {
+            my_dst = ft.grad + id * (int64_t)dim;
+            if (ft.touched) atomicOr(ft.touched + (id >> 5), 1u << (id & 31));
+          }
+          my_coef = coef;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < HU; ++u) {
+        float* dst = reinterpret_cast<float*>(__shfl_sync(0xffffffffu, (unsigned long long)my_dst, gbase + (u < RES ? u : 0)));
+        const float coef = __shfl_sync(0xffffffffu, my_coef, gbase + (u < RES ? u : 0));
+        if (u >= RES || l0 + u >= total_hot || !live) continue;
+        const LookupMeta m = meta[l0 + u];
+        if (sub >= m.nchunk) continue;
+        if (m.flags & 1) gcur = ldg_nc_f4(gout + b * p.out_ld + m.out_off + sub * 4);     // the feature's gradient chunk, once
+        if (dst != nullptr)
+          atomicAdd(reinterpret_cast<float4*>(dst + sub * 4), make_float4(coef * gcur.x, coef * gcur.y, coef * gcur.z, coef * gcur.w));
+      }
+    }
+  }
+}
+
 int fill_params(GatherParams& p, const krs_feature_t* features, int F, int64_t B, float* out, int64_t out_ld) {
   KRS_REQUIRE(features != nullptr && F > 0 && F <= MAXF, "gather: need 1..%d features per call, got %d", MAXF, F);
   KRS_REQUIRE(B >= 0, "gather: negative batch");
@@ -825,7 +943,18 @@ extern "C" int krs_gather_bwd(const krs_feature_t* features, int F, int64_t B, c
       const krs_feature_t& f = p.f[i];
       if (f.dim % 4 != 0 || f.out_offset % 4 != 0 || (f.num_shards <= 1 && !aligned16(f.grad))) vec = false;
     }
-    scatter_generic_kernel<<<grid, 256, 0, s>>>(p, vec);
+    int maxE = 0;
+    int64_t total_hot = 0;
+    for (int i = 0; i < F; ++i) { maxE = max(maxE, p.f[i].dim); total_hot += p.f[i].hotness; }
+    if (vec && maxE <= 128 && total_hot <= SAMPLE_MAXL) {
+      int lpr = 1;
+      while (lpr < maxE / 4 && lpr < 32) lpr <<= 1;
+      const int64_t warps_needed = ceil_div<int64_t>(B, 32 / lpr);
+      const unsigned g2 = (unsigned)krs::imax<int64_t>(1, krs::imin<int64_t>(ceil_div<int64_t>(warps_needed, 8), (int64_t)sm_count() * 64));
+      scatter_sample_kernel<<<g2, 256, 0, s>>>(p, lpr, (int)total_hot);
+    } else {
+      scatter_generic_kernel<<<grid, 256, 0, s>>>(p, vec);
+    }
   }
   KRS_LAUNCH_CHECK();
   return KRS_OK;
