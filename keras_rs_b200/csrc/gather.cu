@@ -644,8 +644,14 @@ struct FeatScatter {
   int nshards, i64, nchunk, hot, out_off, div_kind;
 };
 
-__global__ void __launch_bounds__(256, 4) scatter_sample_kernel(const __grid_constant__ GatherParams p, int lpr, int total_hot) {
-  constexpr int HU = 4;
+#ifndef KRS_SCAT_HU
+#define KRS_SCAT_HU 4
+#endif
+#ifndef KRS_SCAT_MINB
+#define KRS_SCAT_MINB 4
+#endif
+template <int HU, int MINB>
+__global__ void __launch_bounds__(256, MINB) scatter_sample_kernel(const __grid_constant__ GatherParams p, int lpr, int total_hot) {
   __shared__ FeatScatter sf[MAXF];
   __shared__ LookupMeta meta[SAMPLE_MAXL];
   __shared__ int first[MAXF + 1];
@@ -950,8 +956,11 @@ extern "C" int krs_gather_bwd(const krs_feature_t* features, int F, int64_t B, c
       int lpr = 1;
       while (lpr < maxE / 4 && lpr < 32) lpr <<= 1;
       const int64_t warps_needed = ceil_div<int64_t>(B, 32 / lpr);
-      const unsigned g2 = (unsigned)krs::imax<int64_t>(1, krs::imin<int64_t>(ceil_div<int64_t>(warps_needed, 8), (int64_t)sm_count() * 64));
-      scatter_sample_kernel<<<g2, 256, 0, s>>>(p, lpr, (int)total_hot);
+      #ifndef KRS_SCAT_GRIDMUL
+#define KRS_SCAT_GRIDMUL 64
+#endif
+      const unsigned g2 = (unsigned)krs::imax<int64_t>(1, krs::imin<int64_t>(ceil_div<int64_t>(warps_needed, 8), (int64_t)sm_count() * KRS_SCAT_GRIDMUL));
+      scatter_sample_kernel<KRS_SCAT_HU, KRS_SCAT_MINB><<<g2, 256, 0, s>>>(p, lpr, (int)total_hot);
     } else {
       scatter_generic_kernel<<<grid, 256, 0, s>>>(p, vec);
     }
