@@ -95,18 +95,21 @@ __global__ void __launch_bounds__(256) adamw_scalar_kernel(float* __restrict__ p
   }
 }
 
-// Row-sparse SGD / Adagrad over the touched bitmap.  Each lane fetches one bitmap word (coalesced),
-// then the warp walks the set bits of the 32 words together; a row is updated by the whole warp
-// (lanes stride the row).  The word is cleared afterwards by its owner lane.
+// Row-sparse SGD / Adagrad over the touched bitmap.  A warp takes `wpw` (1..32) consecutive bitmap words per pass — lane j < wpw
+// fetches word j — then walks their set bits together; a row is updated by the whole warp (lanes stride the row).  The word
+// is cleared afterwards by its owner lane.  Rows of one warp are updated one after the other (latency-bound), so the host
+// picks `wpw` small enough to spread the bitmap over ~16 CTAs per SM: with 32 words per warp a 1M-row table at 6 % density
+// ran on 123 CTAs, 63 serial rows per warp, 245 us per table (profiles/r2_launches_c3_dlrm.md).
 __global__ void __launch_bounds__(256) sparse_rows_kernel(float* __restrict__ p, float* __restrict__ acc,
                                                           float* __restrict__ g, uint32_t* __restrict__ touched,
                                                           int64_t nwords, int64_t nrows, int row_len, float lr,
-                                                          float eps, int kind) {
+                                                          float eps, int kind, int wpw) {
   const int lane = threadIdx.x & 31;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t w0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; w0 < nwords; w0 += nwarps * 32) {
+  for (int64_t w0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * wpw; w0 < nwords; w0 += nwarps * wpw) {
     const int64_t wi = w0 + lane;
-    uint32_t word = wi < nwords ? touched[wi] : 0u;
+    const bool mine = lane < wpw && wi < nwords;
+    uint32_t word = mine ? touched[wi] : 0u;
     unsigned nz = __ballot_sync(0xffffffffu, word != 0u);
     while (nz) {
       const int src = __ffs(nz) - 1;
@@ -132,7 +135,7 @@ __global__ void __launch_bounds__(256) sparse_rows_kernel(float* __restrict__ p,
         }
       }
     }
-    if (wi < nwords && word != 0u) touched[wi] = 0u;
+    if (mine && word != 0u) touched[wi] = 0u;
   }
 }
 
@@ -387,9 +390,11 @@ extern "C" int krs_sgd_adagrad(float* p, float* acc, float* g, uint32_t* touched
   if (touched) {
     const int64_t rows = n / row_len;
     const int64_t nwords = ceil_div<int64_t>(rows, 32);
-    const unsigned grid =
-        (unsigned)krs::imax<int64_t>(1, krs::imin<int64_t>(ceil_div<int64_t>(ceil_div<int64_t>(nwords, 32), 8), (int64_t)sm_count() * 16));
-    sparse_rows_kernel<<<grid, 256, 0, s>>>(p, acc, g, touched, nwords, rows, row_len, lr, eps, kind);
+    const int64_t max_ctas = (int64_t)sm_count() * 16;
+    int wpw = 32;                                          // words per warp and pass: halve until the grid fills the GPU
+    while (wpw > 1 && ceil_div<int64_t>(ceil_div<int64_t>(nwords, wpw), 8) < max_ctas) wpw >>= 1;
+    const unsigned grid = (unsigned)krs::imax<int64_t>(1, krs::imin<int64_t>(ceil_div<int64_t>(ceil_div<int64_t>(nwords, wpw), 8), max_ctas));
+    sparse_rows_kernel<<<grid, 256, 0, s>>>(p, acc, g, touched, nwords, rows, row_len, lr, eps, kind, wpw);
   } else {
     const unsigned grid = (unsigned)krs::imax<int64_t>(1, krs::imin<int64_t>(ceil_div<int64_t>(n, 256), (int64_t)sm_count() * 32));
     dense_sgd_adagrad_kernel<<<grid, 256, 0, s>>>(p, acc, g, n, lr, eps, kind);

@@ -107,3 +107,42 @@ class DLRM(torch.nn.Module):
         loss.backward()
         optimizer.apply(params)
         return loss.detach()
+
+    def train_on_batch_graph(self, dense, ids, labels, optimizer: optimizers.Optimizer) -> torch.Tensor:
+        """The step of train_on_batch replayed from a CUDA graph captured on first use (per batch shape and optimizer).
+        The eager step is host-bound here (public layers through autograd: ~150 launches whose Python dispatch takes longer
+        than the kernels run); the replay is one launch.  Inputs are copied into the graph's static buffers, the returned
+        loss tensor is the graph's (valid until the next replay).  AdamW / Adam read step and bias correction from the
+        optimizer's device-resident hyper-parameters; lazy Adam (`sparse_rows=True`) computes them on the host and is refused."""
+        if getattr(optimizer, "sparse_rows", False):
+            raise ValueError("train_on_batch_graph: lazy Adam (sparse_rows=True) takes its bias correction from the host step counter "
+                             "and cannot be replayed; use train_on_batch")
+        if not hasattr(self, "_graphs"):
+            self._graphs = {}
+        key = (tuple(dense.shape), tuple(ids.shape), ids.dtype, id(optimizer))
+        st = self._graphs.get(key)
+        if st is None:
+            optimizer.enable_device_hyper(self.device_)
+            s_dense, s_ids, s_y = dense.clone(), ids.clone(), labels.clone()
+            # this batch's step runs eagerly (library one-time initialisation, optimizer slots, arenas); the graph captured
+            # right after it serves every later batch of this shape
+            loss = self.train_on_batch(s_dense, s_ids, s_y, optimizer)
+            torch.cuda.synchronize()
+            params = self.parameters_list()
+            optimizer.zero_grad(params)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                pred = self.forward(s_dense, s_ids, sparse_arena=True)
+                g_loss = ops.loss_fn(pred, s_y, "bce")
+                g_loss.backward()
+                optimizer.apply(params)
+            optimizer.iterations -= 1          # capturing does not execute: the host step counter stays where it was
+            self._graphs[key] = (g, s_dense, s_ids, s_y, g_loss.detach())
+            return loss
+        g, s_dense, s_ids, s_y, g_loss = st
+        s_dense.copy_(dense, non_blocking=True)
+        s_ids.copy_(ids, non_blocking=True)
+        s_y.copy_(labels, non_blocking=True)
+        g.replay()
+        optimizer.iterations += 1
+        return g_loss

@@ -586,10 +586,10 @@ def test_adamw_cold_rows_are_bitwise_equal_to_the_dense_update(K):
         assert float(arena.abs().max()) == 0.0 and int(touched.abs().max()) == 0
 
 
+@pytest.mark.parametrize("V,E,nrows", [(1000, 32, 50), (1_300_003, 8, 5000), (5_000_000, 4, 20000)])   # 1 / 2 / 8 bitmap words per warp
 @pytest.mark.parametrize("name", ["sgd", "adagrad"])
-def test_sparse_rows_optimizers(K, name):
+def test_sparse_rows_optimizers(K, name, V, E, nrows):
     rng = np.random.default_rng(52)
-    V, E = 1000, 32
     p0 = rng.normal(size=(V, E)).astype(np.float32)
     mk = (lambda: K.optimizers.SGD(0.1)) if name == "sgd" else (lambda: K.optimizers.Adagrad(0.05))
     opt_d, opt_a = mk(), mk()
@@ -599,15 +599,14 @@ def test_sparse_rows_optimizers(K, name):
     pa._krs_arena, pa._krs_touched = arena, touched
     p, acc = p0.copy(), np.full_like(p0, 0.1)
     for step in range(3):
-        rows = rng.choice(V, size=50, replace=False)
+        rows = rng.choice(V, size=nrows, replace=False)
         g = np.zeros_like(p0)
-        g[rows] = rng.normal(size=(50, E)).astype(np.float32)
+        g[rows] = rng.normal(size=(nrows, E)).astype(np.float32)
         pd_.grad = dev(g)
         opt_d.apply([pd_])
         arena.copy_(dev(g))
         bits = np.zeros(((V + 31) // 32,), np.uint32)
-        for r in rows:
-            bits[r >> 5] |= np.uint32(1 << (r & 31))
+        np.bitwise_or.at(bits, rows >> 5, (np.uint32(1) << (rows & 31).astype(np.uint32)))
         touched.copy_(dev(bits.view(np.int32)))
         opt_a.apply([pa])
         if name == "sgd":

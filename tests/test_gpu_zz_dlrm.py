@@ -82,3 +82,37 @@ def test_dlrm_train_step_moves_every_parameter():
         l1 = float(m.train_on_batch(dense, ids, y, opt))
     assert np.isfinite(l0) and l1 < l0                                   # fitting one batch reduces its loss
     assert all(float((a - b.detach()).abs().max()) > 0 for a, b in zip(before, m.parameters_list()))
+
+
+@pytest.mark.parametrize("opt_name", ["adagrad", "adamw", "sgd"])
+@pytest.mark.parametrize("interaction", ["dot", "cross"])
+def test_dlrm_cuda_graph_step_matches_eager_step(interaction, opt_name):
+    """train_on_batch_graph (one graph replay per step) must leave the same parameters as the eager launch sequence."""
+    import keras_rs_b200 as K
+    from keras_rs_b200.dlrm import DLRM
+    rng = np.random.default_rng(5)
+    vocab, E, B = [40, 20, 30], 32, 64
+    mk = lambda: DLRM(vocab, embedding_dim=E, bottom_mlp_dims=(16, E), top_mlp_dims=(16, 1), interaction=interaction,
+                      num_dcn_layers=2, dcn_projection_dim=8, seed=1)
+    mk_opt = {"adagrad": lambda: K.optimizers.Adagrad(0.05), "adamw": lambda: K.optimizers.AdamW(0.01),
+              "sgd": lambda: K.optimizers.SGD(0.05)}[opt_name]
+    m1, m2, o1, o2 = mk(), mk(), mk_opt(), mk_opt()
+    for step in range(5):
+        dense = dev(rng.uniform(0, 0.9, size=(B, 13)).astype(np.float32))
+        ids = dev(np.stack([rng.integers(0, v, size=B) for v in vocab], axis=1).astype(np.int32))
+        y = dev(rng.integers(0, 2, size=B).astype(np.float32))
+        l1 = float(m1.train_on_batch(dense, ids, y, o1))
+        l2 = float(m2.train_on_batch_graph(dense, ids, y, o2))
+        np.testing.assert_allclose(l1, l2, rtol=1e-5)
+    assert o1.iterations == o2.iterations == 5
+    for a, b in zip(m1.parameters_list(), m2.parameters_list()):
+        assert_close(npy(b), npy(a), rel=1e-5, what=f"{interaction}/{opt_name} parameter after 5 graph steps")
+
+
+def test_dlrm_cuda_graph_step_refuses_lazy_adam():
+    import keras_rs_b200 as K
+    from keras_rs_b200.dlrm import DLRM
+    m = DLRM([8, 8], embedding_dim=32, bottom_mlp_dims=(16, 32), top_mlp_dims=(16, 1), seed=1)
+    z = lambda *s: torch.zeros(s, device="cuda")
+    with pytest.raises(ValueError, match="lazy Adam"):
+        m.train_on_batch_graph(z(4, 13), torch.zeros((4, 2), dtype=torch.int32, device="cuda"), z(4), K.optimizers.Adam(sparse_rows=True))
