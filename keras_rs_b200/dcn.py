@@ -16,7 +16,6 @@ an optimizer step is two launches.
 """
 from __future__ import annotations
 
-import ctypes as C
 from typing import Sequence
 
 import torch

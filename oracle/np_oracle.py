@@ -27,7 +27,7 @@ ties broken lowest-index-first (jax.lax.top_k behaviour).
 from __future__ import annotations
 
 import math
-from typing import Callable, Sequence
+from typing import Sequence
 
 import numpy as np
 
