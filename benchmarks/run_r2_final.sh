@@ -26,7 +26,7 @@ for row in rd[2:]:
   head -c 900 gpurun_out/r2_final_ncu_$name.txt
 }
 cap gather_scatter '(gather_fast|scatter_fast)_kernel' 2 2 python bench.py --steps 1 --warmup 1 --no-cpu-baseline
-cap multihot '(gather_sample|scatter_generic)_kernel' 2 2 python benchmarks/bench_kernels.py --what multihot --reps 2
+cap multihot '(gather_sample|scatter_sample)_kernel' 2 2 python benchmarks/bench_kernels.py --what multihot --reps 2
 cap dot 'dot_(fwd|bwd)_mma_kernel' 6 2 python benchmarks/bench_kernels.py --what dot --reps 2
 timeout 280 compute-sanitizer --tool memcheck --print-limit 20 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_exchange.py tests/test_retrieval_helpers.py -q -p no:cacheprovider -x -k "gather or scatter or route or slot or compact or row_topk or hard_negative or accidental or multihot or embed" > gpurun_out/r2_final_sanitizer_memcheck_kernels.log 2>&1; grep -E "ERROR SUMMARY|passed|failed" gpurun_out/r2_final_sanitizer_memcheck_kernels.log | tail -3
 ls -la gpurun_out | grep r2_final
